@@ -1,0 +1,906 @@
+// inflate_kernel.cu -- batched DEFLATE / zlib / gzip decompression for sm_100a.
+//
+// What it computes: for every chunk i of the batch, exactly what
+//   libdeflate_{deflate,zlib,gzip}_decompress_ex()   (ref: lib/decompress_template.h:44-772,
+//   lib/deflate_decompress.c:105-297,721-1004, lib/gzip_decompress.c:32-134,
+//   lib/zlib_decompress.c:32-94)
+// would return for (in[i], in_nbytes[i], out[i], out_avail[i]): the decoded bytes,
+// the enum libdeflate_result verdict, actual_in and actual_out.  Only those are
+// contractual; table geometry, refill policy and scheduling below are ours.
+//
+// B200 mapping -- "one lane per stream", because Huffman decoding is a bit-serial
+// dependency chain and only issue slots spent on *different* streams add up:
+//   * a warp decodes 32 independent chunks at once, one per lane; a lane that
+//     finishes its chunk pulls the next chunk index from a global counter, so
+//     lanes never idle on a tail;
+//   * each lane's decode tables live in shared memory, lane-interleaved
+//     (entry i of lane t sits in bank t), so the 32 data-dependent lookups of a
+//     warp instruction are bank-conflict free by construction;
+//   * tables are compact 16-bit entries: 9-bit main litlen table + 128 subtable
+//     entries, 6-bit main offset table + 64 subtable entries = 1536 B per lane,
+//     48 KiB per warp, 4 warps per SM; the (rare) excess subtable entries of an
+//     adversarial code spill to a per-lane global scratch;
+//   * block headers are parsed by the owning lane, then the WARP builds that
+//     lane's tables cooperatively (ballot/match_any ranking, strided fills);
+//   * stored blocks are copied by the whole warp, coalesced;
+//   * compressed input is consumed through 4-byte aligned loads with one word
+//     of lookahead per lane; output is gathered in a per-lane 8-byte accumulator
+//     and written with aligned 8-byte stores; match sources are fetched with
+//     aligned 8-byte loads + funnel shifts (offset >= 8) or expanded in
+//     registers from the periodic pattern (offset < 8).
+//
+// Verdict rules restated from the reference in terms of P = number of input bits
+// consumed and n = in_nbytes (see DESIGN.md "verdict algebra"):
+//   - the input is virtually followed by zero bytes (deflate_decompress.c:214-254);
+//   - at the start of every litlen symbol: P >= 8n+9  =>  BAD_DATA (the refill at
+//     the top of the generic loop would have over-read more than 8 bytes);
+//   - literal with no room => INSUFFICIENT_SPACE; match: length > room =>
+//     INSUFFICIENT_SPACE *before* the offset is looked at, then offset > bytes
+//     produced => BAD_DATA (decompress_template.h:696-727);
+//   - at the end of the final block: P > 8n => BAD_DATA (decompress_template.h:754);
+//   - stored block: bits up to the byte boundary must be real (<= 8n), 4 header
+//     bytes must exist, LEN == ~NLEN, then room (INSUFFICIENT_SPACE), then LEN
+//     bytes must exist (decompress_template.h:255-283).
+//
+// Algorithmic HBM bytes per chunk: in_nbytes (read once) + actual_out (written
+// once).  Back-reference reads are window traffic served by L1/L2.
+#include "ldb_common.cuh"
+
+#define INF_LB        9			// main litlen table bits
+#define INF_LMAIN     (1 << INF_LB)
+#define INF_LSUB_SM   128		// litlen subtable entries kept in shared memory
+#define INF_LSUB_CAP  1024		// total litlen subtable capacity (rest in global scratch)
+#define INF_OB        6			// main offset table bits
+#define INF_OMAIN     (1 << INF_OB)
+#define INF_OSUB_SM   64
+#define INF_OSUB_CAP  1024
+#define INF_L_ENTRIES (INF_LMAIN + INF_LSUB_SM)		// 640 u16 per lane
+#define INF_O_ENTRIES (INF_OMAIN + INF_OSUB_SM)		// 128 u16 per lane
+#define INF_L_WORDS   (INF_L_ENTRIES / 2)		// 320 words per lane
+#define INF_O_WORDS   (INF_O_ENTRIES / 2)		// 64 words per lane
+#define INF_OVF_L     (INF_LSUB_CAP - INF_LSUB_SM)	// 896 u16
+#define INF_OVF_O     (INF_OSUB_CAP - INF_OSUB_SM)	// 960 u16
+#define INF_OVF_ENTRIES (INF_OVF_L + INF_OVF_O)
+
+#define INF_QUANTUM   192		// decode iterations between service phases
+
+// per-warp shared memory layout (bytes)
+#define INF_SM_LTAB    0
+#define INF_SM_OTAB    (INF_SM_LTAB + INF_L_WORDS * 32 * 4)	// 40960
+#define INF_SM_SCRATCH (INF_SM_OTAB + INF_O_WORDS * 32 * 4)	// 49152
+#define INF_SM_CNT     (INF_SM_SCRATCH)				// u32[16]
+#define INF_SM_CODE    (INF_SM_CNT + 64)			// u32[16]
+#define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[512]
+#define INF_SM_BYTES   (INF_SM_SUBBITS + 512)			// 49792
+
+// entry encodings (u16)
+#define LE_LEN_FLAG  0x4000u
+#define LE_EOB_FLAG  0x8000u
+#define LE_SUB_FLAG  0xC000u
+#define OE_SUB_FLAG  0x8000u
+
+enum { ST_IDLE = 0, ST_HEADER = 1, ST_BUILD = 2, ST_STORED = 3, ST_DECODE = 4 };
+
+size_t ldb_inflate_overflow_bytes_per_stream(void) { return INF_OVF_ENTRIES * sizeof(u16); }
+
+struct inf_lane {
+	// input
+	const u8 *in;		// start of the DEFLATE stream (after any wrapper header)
+	u32 in_n;		// bytes of DEFLATE data available
+	u32 in_pos;		// bytes appended to bitbuf so far (may exceed in_n: virtual zeros)
+	u64 bitbuf;
+	u32 bitcnt;
+	u32 next_word;
+	// output
+	u8 *out;
+	u32 out_pos;
+	u32 out_avail;
+	u64 acc;		// bytes of the current aligned output word produced so far
+	// block state
+	u32 state;
+	u32 is_final;
+	u32 hlit, hdist, is_static;
+	u32 stored_len;
+	// bookkeeping
+	u32 chunk;		// chunk index
+	u32 hdr_bytes;		// wrapper header size
+};
+
+// ---- lane-interleaved table access ------------------------------------------
+__device__ __forceinline__ u32 tab_idx(u32 entry, u32 lane) { return (((entry >> 1) << 5) + lane) * 2 + (entry & 1); }
+__device__ __forceinline__ u32 byte_idx(u32 i, u32 lane) { return (((i >> 2) << 5) + lane) * 4 + (i & 3); }
+
+// ---- bit reader ---------------------------------------------------------------
+__device__ __forceinline__ u32 inf_ld_word(const u8 *in, u32 pos, u32 n)
+{
+	if (pos + 4 <= n && pos + 4 >= 4)
+		return *(const u32 *)(in + pos);
+	u32 w = 0;
+	for (u32 i = 0; i < 4; i++)
+		if (pos + i < n && pos + i >= pos) w |= (u32)in[pos + i] << (8 * i);
+	return w;
+}
+
+__device__ __forceinline__ void inf_bits_init(inf_lane &s, u32 pos)
+{
+	s.bitbuf = 0;
+	s.bitcnt = 0;
+	s.in_pos = pos;
+	// byte steps until the load address is 4-byte aligned
+	while ((((uintptr_t)s.in + s.in_pos) & 3) != 0) {
+		u32 b = s.in_pos < s.in_n ? s.in[s.in_pos] : 0;
+		s.bitbuf |= (u64)b << s.bitcnt;
+		s.bitcnt += 8;
+		s.in_pos++;
+	}
+	s.next_word = inf_ld_word(s.in, s.in_pos, s.in_n);
+}
+
+__device__ __forceinline__ void inf_refill(inf_lane &s)
+{
+	if (s.bitcnt < 32) {
+		s.bitbuf |= (u64)s.next_word << s.bitcnt;
+		s.bitcnt += 32;
+		s.in_pos += 4;
+		s.next_word = inf_ld_word(s.in, s.in_pos, s.in_n);
+	}
+}
+
+__device__ __forceinline__ u32 inf_take(inf_lane &s, u32 nbits)
+{
+	u32 v = (u32)s.bitbuf & ((1u << nbits) - 1);
+	s.bitbuf >>= nbits;
+	s.bitcnt -= nbits;
+	return v;
+}
+
+// P = bits consumed so far
+__device__ __forceinline__ u64 inf_bits_consumed(const inf_lane &s) { return (u64)s.in_pos * 8 - s.bitcnt; }
+
+// ---- output -------------------------------------------------------------------
+// acc holds the already produced bytes of the aligned 8-byte word that contains
+// out_pos (zero elsewhere).  A completed word is stored at once.
+__device__ __forceinline__ void inf_store_word(const inf_lane &s, u32 pos_end, u64 w)
+{
+	// word covers absolute addresses [A, A+8), A+8 == out + pos_end rounded: pos_end is
+	// the out position just past the last byte of the word that is valid.
+	uintptr_t a_end = (uintptr_t)s.out + pos_end;		// one past last valid byte
+	uintptr_t A = (a_end - 1) & ~(uintptr_t)7;
+	if (A >= (uintptr_t)s.out && A + 8 <= (uintptr_t)s.out + s.out_avail) {
+		*(u64 *)A = w;
+	} else {
+		uintptr_t lo = A < (uintptr_t)s.out ? (uintptr_t)s.out : A;
+		for (uintptr_t p = lo; p < a_end; p++)
+			*(u8 *)p = (u8)(w >> (8 * (p - A)));
+	}
+}
+
+__device__ __forceinline__ void inf_put_byte(inf_lane &s, u32 b)
+{
+	u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
+	s.acc |= (u64)b << (8 * k);
+	s.out_pos++;
+	if (k == 7) {
+		inf_store_word(s, s.out_pos, s.acc);
+		s.acc = 0;
+	}
+}
+
+// make the partial word visible in memory (needed before reading it back)
+__device__ __forceinline__ void inf_flush_partial(const inf_lane &s)
+{
+	u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
+	if (k) inf_store_word(s, s.out_pos, s.acc);
+}
+
+// unaligned 8-byte read of already written output at position pos (pos < out_pos)
+__device__ __forceinline__ u64 inf_read8(const inf_lane &s, u32 pos)
+{
+	uintptr_t a = (uintptr_t)s.out + pos;
+	uintptr_t A = a & ~(uintptr_t)7;
+	u32 sh = (u32)(a & 7) * 8;
+	u64 v0 = *(const volatile u64 *)A;
+	if (sh == 0) return v0;
+	u64 v1 = *(const volatile u64 *)(A + 8);
+	return (v0 >> sh) | (v1 << (64 - sh));
+}
+
+__device__ __forceinline__ void inf_copy_match(inf_lane &s, u32 length, u32 offset)
+{
+	u32 remaining = length;
+	if (offset >= 8) {
+		while (remaining) {
+			u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
+			u32 nb = 8 - k;
+			if (nb > remaining) nb = remaining;
+			u64 src = inf_read8(s, s.out_pos - offset);
+			if (nb < 8) src &= ((u64)1 << (8 * nb)) - 1;
+			s.acc |= src << (8 * k);
+			s.out_pos += nb;
+			remaining -= nb;
+			if (k + nb == 8) {
+				inf_store_word(s, s.out_pos, s.acc);
+				s.acc = 0;
+			}
+		}
+	} else {
+		// periodic source: expand the last 'offset' bytes in registers
+		inf_flush_partial(s);
+		u64 cur = inf_read8(s, s.out_pos - offset);
+		u32 ob = 8 * offset;
+		cur &= ((u64)1 << ob) - 1;
+		cur |= cur << ob;
+		if (2 * ob < 64) cur |= cur << (2 * ob);
+		if (4 * ob < 64) cur |= cur << (4 * ob);
+		while (remaining) {
+			u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
+			u32 nb = 8 - k;
+			if (nb > remaining) nb = remaining;
+			u64 src = cur;
+			if (nb < 8) src &= ((u64)1 << (8 * nb)) - 1;
+			s.acc |= src << (8 * k);
+			s.out_pos += nb;
+			remaining -= nb;
+			if (k + nb == 8) {
+				inf_store_word(s, s.out_pos, s.acc);
+				s.acc = 0;
+			}
+			// advance the pattern by nb bytes
+			u32 r = nb % offset;
+			if (r) cur = (cur >> (8 * r)) | (cur << (8 * (offset - r)));
+		}
+	}
+}
+
+// ---- wrapper headers ------------------------------------------------------------
+// Returns the header size, or 0xffffffff for BAD_DATA.  Sets *footer to the trailer size.
+// ref: lib/gzip_decompress.c:45-98, lib/zlib_decompress.c:45-66
+__device__ u32 inf_parse_wrapper(const u8 *in, size_t n, int format, u32 *footer)
+{
+	*footer = 0;
+	if (format == LDB_FMT_RAW) return 0;
+	if (format == LDB_FMT_ZLIB) {
+		*footer = 4;
+		if (n < 6) return 0xffffffffu;
+		u32 hdr = ((u32)in[0] << 8) | in[1];
+		if (hdr % 31) return 0xffffffffu;
+		if (((hdr >> 8) & 0xf) != 8) return 0xffffffffu;
+		if ((hdr >> 12) > 7) return 0xffffffffu;
+		if ((hdr >> 5) & 1) return 0xffffffffu;
+		return 2;
+	}
+	*footer = 8;
+	if (n < 18) return 0xffffffffu;
+	if (in[0] != 0x1f || in[1] != 0x8b || in[2] != 8) return 0xffffffffu;
+	u32 flg = in[3];
+	size_t pos = 10;
+	if (flg & 0xE0) return 0xffffffffu;
+	if (flg & 0x04) {	// FEXTRA
+		u32 xlen = in[pos] | ((u32)in[pos + 1] << 8);
+		pos += 2;
+		if (n - pos < (size_t)xlen + 8) return 0xffffffffu;
+		pos += xlen;
+	}
+	if (flg & 0x08) {	// FNAME
+		while (in[pos++] != 0 && pos != n) {}
+		if (n - pos < 8) return 0xffffffffu;
+	}
+	if (flg & 0x10) {	// FCOMMENT
+		while (in[pos++] != 0 && pos != n) {}
+		if (n - pos < 8) return 0xffffffffu;
+	}
+	if (flg & 0x02) {	// FHCRC
+		pos += 2;
+		if (pos > n || n - pos < 8) return 0xffffffffu;
+	}
+	return (u32)pos;
+}
+
+// ---- per-lane header parsing ----------------------------------------------------
+// Parses one block header.  Dynamic: leaves the 320 code lengths as bytes in the
+// lane's litlen table region and moves to ST_BUILD.  Returns a verdict != SUCCESS
+// to abort the stream.
+__device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
+{
+	u8 *lens = sm + INF_SM_LTAB;		// byte_idx(i, lane)
+	u8 *pretab = sm + INF_SM_OTAB;		// byte_idx(i, lane), 128 entries
+	static const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+	inf_refill(s);
+	s.is_final = inf_take(s, 1);
+	u32 btype = inf_take(s, 2);
+
+	if (btype == DEFLATE_BLOCKTYPE_DYNAMIC) {
+		s.hlit = 257 + inf_take(s, 5);
+		s.hdist = 1 + inf_take(s, 5);
+		u32 hclen = 4 + inf_take(s, 4);
+		s.is_static = 0;
+
+		// precode lengths (ref: decompress_template.h:108-145)
+		u32 plen[19];
+		for (int i = 0; i < 19; i++) plen[i] = 0;
+		u32 cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		u64 packed = 0;		// 19 x 3 bits, indexed by symbol
+		for (u32 i = 0; i < hclen; i++) {
+			inf_refill(s);
+			u32 l = inf_take(s, 3);
+			packed |= (u64)l << (3 * perm[i]);
+		}
+		for (int sym = 0; sym < 19; sym++) {
+			plen[sym] = (u32)(packed >> (3 * sym)) & 7;
+			cnt[plen[sym]]++;
+		}
+		// precode table (ref: build_decode_table semantics, deflate_decompress.c:721-853)
+		u32 maxlen = 7;
+		while (maxlen > 1 && cnt[maxlen] == 0) maxlen--;
+		u32 used = 0;
+		for (u32 l = 1; l <= maxlen; l++) used = (used << 1) + cnt[l];
+		if (used > (1u << maxlen)) return LDB_BAD_DATA;
+		if (used < (1u << maxlen)) {
+			u32 sym = 0;
+			if (used != 0) {
+				if (used != (1u << (maxlen - 1)) || cnt[1] != 1) return LDB_BAD_DATA;
+				for (int q = 0; q < 19; q++)
+					if (plen[q] == 1) { sym = q; break; }
+			}
+			for (u32 i = 0; i < 128; i++) pretab[byte_idx(i, lane)] = (u8)((sym << 3) | 1);
+		} else {
+			u32 code = 0;
+			for (u32 l = 1; l <= maxlen; l++) {
+				for (u32 sym = 0; sym < 19; sym++) {
+					if (plen[sym] != l) continue;
+					u32 rev = __brev(code) >> (32 - l);
+					for (u32 i = rev; i < 128; i += 1u << l)
+						pretab[byte_idx(i, lane)] = (u8)((sym << 3) | l);
+					code++;
+				}
+				code <<= 1;
+			}
+		}
+
+		// litlen + offset code lengths (ref: decompress_template.h:151-245)
+		u32 total = s.hlit + s.hdist;
+		u32 i = 0;
+		u32 prev = 0;
+		while (i < total) {
+			inf_refill(s);
+			u32 e = pretab[byte_idx((u32)s.bitbuf & 127, lane)];
+			u32 l = e & 7;
+			s.bitbuf >>= l;
+			s.bitcnt -= l;
+			u32 presym = e >> 3;
+			if (presym < 16) {
+				lens[byte_idx(i, lane)] = (u8)presym;
+				prev = presym;
+				i++;
+				continue;
+			}
+			u32 rep, val;
+			if (presym == 16) {
+				if (i == 0) return LDB_BAD_DATA;
+				rep = 3 + inf_take(s, 2);
+				val = prev;
+			} else if (presym == 17) {
+				rep = 3 + inf_take(s, 3);
+				val = 0;
+			} else {
+				rep = 11 + inf_take(s, 7);
+				val = 0;
+			}
+			// running past the announced count is an error (decompress_template.h:245)
+			if (i + rep > total) return LDB_BAD_DATA;
+			for (u32 k = 0; k < rep; k++) lens[byte_idx(i + k, lane)] = (u8)val;
+			prev = val;
+			i += rep;
+		}
+		s.state = ST_BUILD;
+		return LDB_SUCCESS;
+	}
+
+	if (btype == DEFLATE_BLOCKTYPE_STORED) {
+		// ref: decompress_template.h:247-285
+		u64 P = inf_bits_consumed(s);
+		u64 Pa = (P + 7) & ~(u64)7;
+		if (Pa > (u64)s.in_n * 8) return LDB_BAD_DATA;
+		u32 B = (u32)(Pa >> 3);
+		if (s.in_n - B < 4) return LDB_BAD_DATA;
+		u32 len = s.in[B] | ((u32)s.in[B + 1] << 8);
+		u32 nlen = s.in[B + 2] | ((u32)s.in[B + 3] << 8);
+		if (len != (nlen ^ 0xffffu)) return LDB_BAD_DATA;
+		if (len > s.out_avail - s.out_pos) return LDB_INSUFFICIENT_SPACE;
+		if (len > s.in_n - (B + 4)) return LDB_BAD_DATA;
+		s.in_pos = B + 4;	// source position of the raw bytes
+		s.stored_len = len;
+		s.state = ST_STORED;
+		return LDB_SUCCESS;
+	}
+
+	if (btype != DEFLATE_BLOCKTYPE_STATIC) return LDB_BAD_DATA;
+	s.hlit = 288;
+	s.hdist = 32;
+	s.is_static = 1;
+	s.state = ST_BUILD;
+	return LDB_SUCCESS;
+}
+
+// ---- cooperative table construction ------------------------------------------------
+// All 32 lanes build the decode table of ONE code for lane 'owner'.
+//   mylen[r] : code length of symbol r*32+lane (0 = unused), r < nrows
+//   is_litlen: entry encoding selector
+// Returns false for an invalid code (overfull, or incomplete beyond the two
+// accepted cases of deflate_decompress.c:804-853).
+template <int NROWS, int MAINBITS, int SUB_SM, int SUB_CAP, bool IS_LITLEN>
+__device__ bool inf_build_table(const u32 (&mylen)[NROWS], u8 *sm, u32 tab_off, u16 *ovf, u32 owner, u32 lane)
+{
+	u32 *cnt = (u32 *)(sm + INF_SM_CNT);
+	u32 *nextcode = (u32 *)(sm + INF_SM_CODE);
+	u8 *subbits = sm + INF_SM_SUBBITS;
+	u16 *tab = (u16 *)(sm + tab_off);
+	const u32 lt_mask = (1u << lane) - 1;
+
+	if (lane < 16) cnt[lane] = 0;
+	for (u32 i = lane; i < (1u << MAINBITS); i += 32) subbits[i] = 0;
+	__syncwarp();
+#pragma unroll
+	for (int r = 0; r < NROWS; r++) {
+		u32 l = mylen[r];
+		u32 m = __match_any_sync(LDB_FULL_MASK, l);
+		if (l && (m & lt_mask) == 0) cnt[l] += __popc(m);
+		__syncwarp();
+	}
+	u32 mycnt = (lane >= 1 && lane < 16) ? cnt[lane] : 0;
+	u32 usedmask = __ballot_sync(LDB_FULL_MASK, mycnt != 0);
+	u32 maxlen = usedmask ? 31 - __clz(usedmask) : 1;
+	u32 contrib = (lane >= 1 && lane <= maxlen) ? (mycnt << (maxlen - lane)) : 0;
+	for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(LDB_FULL_MASK, contrib, o);
+	const u32 used = contrib;
+	if (used > (1u << maxlen)) return false;
+
+	auto make_entry = [&](u32 sym, u32 len) -> u32 {
+		if (IS_LITLEN) {
+			if (sym < 256) return (sym << 4) | len;
+			if (sym == 256) return LE_EOB_FLAG | len;
+			u32 slot = sym - 257;
+			if (slot > 28) slot = 28;	// syms 286/287 decode as length 258 (deflate_decompress.c:587)
+			return LE_LEN_FLAG | (slot << 4) | len;
+		} else {
+			u32 slot = sym > 29 ? 29 : sym;	// syms 30/31 decode as base 24577 (deflate_decompress.c:627)
+			return (slot << 4) | len;
+		}
+	};
+
+	if (used < (1u << maxlen)) {
+		// incomplete code: only "empty" and "one codeword of length 1" are accepted
+		u32 sym = 0;
+		if (used != 0) {
+			if (used != (1u << (maxlen - 1)) || cnt[1] != 1) return false;
+			u32 mine = 0xffffffffu;
+#pragma unroll
+			for (int r = 0; r < NROWS; r++)
+				if (mylen[r] == 1 && mine == 0xffffffffu) mine = r * 32 + lane;
+			for (int o = 16; o > 0; o >>= 1) {
+				u32 other = __shfl_xor_sync(LDB_FULL_MASK, mine, o);
+				if (other < mine) mine = other;
+			}
+			sym = mine;
+		}
+		u32 e = make_entry(sym, 1);
+		for (u32 i = lane; i < (1u << MAINBITS); i += 32) tab[tab_idx(i, owner)] = (u16)e;
+		__syncwarp();
+		return true;
+	}
+
+	// canonical first codes (MSB-first numeric): code[l+1] = (code[l] + cnt[l]) << 1
+	if (lane == 0) {
+		u32 code = 0;
+		for (u32 l = 1; l <= 15; l++) {
+			nextcode[l] = code;
+			code = (code + cnt[l]) << 1;
+		}
+	}
+	__syncwarp();
+
+	u32 mycode[NROWS];
+#pragma unroll
+	for (int r = 0; r < NROWS; r++) {
+		u32 l = mylen[r];
+		u32 m = __match_any_sync(LDB_FULL_MASK, l);
+		u32 c = 0;
+		if (l) {
+			c = nextcode[l] + __popc(m & lt_mask);
+		}
+		__syncwarp();
+		if (l && (m & lt_mask) == 0) nextcode[l] += __popc(m);
+		__syncwarp();
+		mycode[r] = c;
+	}
+
+	// pass 1: short codes fill the main table, long codes vote for subtable sizes
+	bool any_long = false;
+#pragma unroll
+	for (int r = 0; r < NROWS; r++) {
+		u32 l = mylen[r];
+		if (!l) continue;
+		u32 rev = __brev(mycode[r]) >> (32 - l);
+		u32 sym = r * 32 + lane;
+		if (l <= MAINBITS) {
+			u32 e = make_entry(sym, l);
+			for (u32 i = rev; i < (1u << MAINBITS); i += 1u << l) tab[tab_idx(i, owner)] = (u16)e;
+		} else {
+			any_long = true;
+			u32 prefix = rev & ((1u << MAINBITS) - 1);
+			// byte-wide max via a 32-bit atomic on the containing word
+			u32 *w = (u32 *)(subbits + (prefix & ~3u));
+			u32 sh = (prefix & 3) * 8;
+			u32 want = l - MAINBITS;
+			u32 old = *w;
+			while (((old >> sh) & 0xff) < want) {
+				u32 assumed = old;
+				u32 nv = (old & ~(0xffu << sh)) | (want << sh);
+				old = atomicCAS(w, assumed, nv);
+				if (old == assumed) break;
+			}
+		}
+	}
+	if (!__any_sync(LDB_FULL_MASK, any_long)) {
+		__syncwarp();
+		return true;
+	}
+	__syncwarp();
+
+	// subtable allocation: lane handles a contiguous run of main prefixes
+	const u32 per_lane = (1u << MAINBITS) / 32;
+	u32 mysum = 0;
+	for (u32 j = 0; j < per_lane; j++) {
+		u32 sb = subbits[lane * per_lane + j];
+		if (sb) mysum += 1u << sb;
+	}
+	u32 incl = mysum;
+	for (int o = 1; o < 32; o <<= 1) {
+		u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o);
+		if (lane >= (u32)o) incl += t;
+	}
+	u32 total = __shfl_sync(LDB_FULL_MASK, incl, 31);
+	if (total > SUB_CAP) return false;	// cannot happen for a complete canonical code
+	u32 start = incl - mysum;
+	for (u32 j = 0; j < per_lane; j++) {
+		u32 p = lane * per_lane + j;
+		u32 sb = subbits[p];
+		if (sb) {
+			u32 e = (IS_LITLEN ? LE_SUB_FLAG : OE_SUB_FLAG) | (start << 4) | sb;
+			tab[tab_idx(p, owner)] = (u16)e;
+			start += 1u << sb;
+		}
+	}
+	__syncwarp();
+
+	// pass 2: long codes fill their subtables
+#pragma unroll
+	for (int r = 0; r < NROWS; r++) {
+		u32 l = mylen[r];
+		if (l <= MAINBITS) continue;
+		u32 rev = __brev(mycode[r]) >> (32 - l);
+		u32 sym = r * 32 + lane;
+		u32 prefix = rev & ((1u << MAINBITS) - 1);
+		u32 pe = tab[tab_idx(prefix, owner)];
+		u32 sstart = (pe >> 4) & 0x3ff;
+		u32 sb = pe & 15;
+		u32 e = make_entry(sym, l - MAINBITS);
+		for (u32 i = rev >> MAINBITS; i < (1u << sb); i += 1u << (l - MAINBITS)) {
+			u32 idx = sstart + i;
+			if (idx < SUB_SM) tab[tab_idx((1u << MAINBITS) + idx, owner)] = (u16)e;
+			else ovf[idx - SUB_SM] = (u16)e;
+		}
+	}
+	__syncwarp();
+	return true;
+}
+
+// static Huffman code lengths (ref: decompress_template.h:313-323)
+__device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
+{
+	return sym < 144 ? 8 : (sym < 256 ? 9 : (sym < 280 ? 7 : 8));
+}
+
+// ---- one decode step (one litlen symbol, plus the match if it is a length) ----------
+__device__ __forceinline__ int inf_decode_step(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
+{
+	const u16 *ltab = (const u16 *)(sm + INF_SM_LTAB);
+	const u16 *otab = (const u16 *)(sm + INF_SM_OTAB);
+
+	inf_refill(s);
+	if (s.in_pos > s.in_n) {
+		// virtual zero bytes are in play: P >= 8n+9 means the reference's refill
+		// over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
+		if (inf_bits_consumed(s) >= (u64)s.in_n * 8 + 9) return LDB_BAD_DATA;
+	}
+	u32 e = ltab[tab_idx((u32)s.bitbuf & (INF_LMAIN - 1), lane)];
+	if (e >= LE_SUB_FLAG) {
+		u32 sstart = (e >> 4) & 0x3ff;
+		u32 sb = e & 15;
+		s.bitbuf >>= INF_LB;
+		s.bitcnt -= INF_LB;
+		u32 idx = sstart + ((u32)s.bitbuf & ((1u << sb) - 1));
+		e = idx < INF_LSUB_SM ? ltab[tab_idx(INF_LMAIN + idx, lane)] : ovf[idx - INF_LSUB_SM];
+	}
+	u32 cl = e & 15;
+	s.bitbuf >>= cl;
+	s.bitcnt -= cl;
+	if (e < 0x1000) {
+		if (s.out_pos == s.out_avail) return LDB_INSUFFICIENT_SPACE;
+		inf_put_byte(s, e >> 4);
+		return LDB_SUCCESS;
+	}
+	if (e & LE_EOB_FLAG) {
+		s.state = ST_HEADER;	// caller turns this into "done" when is_final
+		return LDB_SUCCESS;
+	}
+	// length (Appendix A table, ref: deflate_decompress.c:576-587)
+	u32 slot = (e >> 4) & 31;
+	u32 length;
+	if (slot < 8) {
+		length = 3 + slot;
+	} else if (slot < 28) {
+		u32 eb = (slot - 4) >> 2;
+		length = 3 + ((4 + (slot & 3)) << eb) + ((u32)s.bitbuf & ((1u << eb) - 1));
+		s.bitbuf >>= eb;
+		s.bitcnt -= eb;
+	} else {
+		length = 258;
+	}
+	if (length > s.out_avail - s.out_pos) return LDB_INSUFFICIENT_SPACE;
+
+	inf_refill(s);
+	u32 oe = otab[tab_idx((u32)s.bitbuf & (INF_OMAIN - 1), lane)];
+	if (oe & OE_SUB_FLAG) {
+		u32 sstart = (oe >> 4) & 0x3ff;
+		u32 sb = oe & 15;
+		s.bitbuf >>= INF_OB;
+		s.bitcnt -= INF_OB;
+		u32 idx = sstart + ((u32)s.bitbuf & ((1u << sb) - 1));
+		oe = idx < INF_OSUB_SM ? otab[tab_idx(INF_OMAIN + idx, lane)] : ovf[INF_OVF_L + idx - INF_OSUB_SM];
+	}
+	u32 ocl = oe & 15;
+	s.bitbuf >>= ocl;
+	s.bitcnt -= ocl;
+	u32 oslot = (oe >> 4) & 31;
+	u32 offset;
+	if (oslot < 4) {
+		offset = 1 + oslot;
+	} else {
+		u32 eb = (oslot - 2) >> 1;
+		offset = 1 + ((2 + (oslot & 1)) << eb) + ((u32)s.bitbuf & ((1u << eb) - 1));
+		s.bitbuf >>= eb;
+		s.bitcnt -= eb;
+	}
+	if (offset > s.out_pos) return LDB_BAD_DATA;
+	inf_copy_match(s, length, offset);
+	return LDB_SUCCESS;
+}
+
+// ---- the kernel ---------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
+{
+	LDB_DYN_SMEM(sm);
+	const u32 lane = threadIdx.x & 31;
+	u16 *ovf = (u16 *)a.overflow_scratch + ((size_t)blockIdx.x * 32 + lane) * INF_OVF_ENTRIES;
+
+	inf_lane s;
+	s.state = ST_IDLE;
+	s.chunk = 0xffffffffu;
+	s.in = nullptr; s.in_n = 0; s.in_pos = 0; s.bitbuf = 0; s.bitcnt = 0; s.next_word = 0;
+	s.out = nullptr; s.out_pos = 0; s.out_avail = 0; s.acc = 0;
+	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.hdr_bytes = 0;
+	bool exhausted = false;
+
+	// finishes the lane's stream with 'verdict' and makes the lane idle
+	auto finish = [&](int verdict) {
+		const size_t c = s.chunk;
+		u32 footer = a.format == LDB_FMT_GZIP ? 8 : (a.format == LDB_FMT_ZLIB ? 4 : 0);
+		if (verdict == LDB_SUCCESS) {
+			// flush the partial output word
+			u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
+			if (k) inf_store_word(s, s.out_pos, s.acc);
+			u64 P = inf_bits_consumed(s);
+			if (P > (u64)s.in_n * 8) verdict = LDB_BAD_DATA;	// decompress_template.h:754
+			else {
+				u32 used = (u32)((P + 7) >> 3);
+				if (a.actual_in) a.actual_in[c] = (size_t)s.hdr_bytes + used + footer;
+				a.actual_out[c] = s.out_pos;
+				if ((a.flags & 1u) && s.out_pos != s.out_avail) verdict = LDB_SHORT_OUTPUT;
+				else if (footer) {
+					const u8 *t = s.in + used;
+					if (a.format == LDB_FMT_GZIP) {
+						a.trailer_expect[c] = t[0] | ((u32)t[1] << 8) | ((u32)t[2] << 16) | ((u32)t[3] << 24);
+						a.isize_expect[c] = t[4] | ((u32)t[5] << 8) | ((u32)t[6] << 16) | ((u32)t[7] << 24);
+					} else {
+						a.trailer_expect[c] = ((u32)t[0] << 24) | ((u32)t[1] << 16) | ((u32)t[2] << 8) | t[3];
+					}
+				}
+			}
+		}
+		if (verdict != LDB_SUCCESS && verdict != LDB_SHORT_OUTPUT) a.actual_out[c] = 0;
+		a.results[c] = verdict;
+		s.state = ST_IDLE;
+	};
+
+	for (;;) {
+		// ---- service phase -------------------------------------------------
+		// (1) idle lanes fetch new chunks
+		u32 idle = __ballot_sync(LDB_FULL_MASK, s.state == ST_IDLE && !exhausted);
+		if (idle) {
+			u32 base = 0;
+			if (lane == (u32)(__ffs(idle) - 1)) base = atomicAdd(work_counter, (u32)__popc(idle));
+			base = __shfl_sync(LDB_FULL_MASK, base, __ffs(idle) - 1);
+			if (s.state == ST_IDLE && !exhausted) {
+				size_t c = (size_t)base + __popc(idle & ((1u << lane) - 1));
+				if (c >= a.n) {
+					exhausted = true;
+				} else {
+					s.chunk = (u32)c;
+					const u8 *in = (const u8 *)a.in_ptrs[c];
+					size_t n = a.in_nbytes[c];
+					s.out = (u8 *)a.out_ptrs[c];
+					size_t oa = a.out_avail[c];
+					s.out_avail = oa > 0xfffffff0u ? 0xfffffff0u : (u32)oa;
+					s.out_pos = 0;
+					s.acc = 0;
+					u32 footer;
+					u32 hdr = inf_parse_wrapper(in, n, a.format, &footer);
+					if (hdr == 0xffffffffu) {
+						a.actual_out[c] = 0;
+						a.results[c] = LDB_BAD_DATA;
+					} else {
+						size_t dn = n - hdr - footer;
+						s.in = in + hdr;
+						s.in_n = dn > 0xfffffff0u ? 0xfffffff0u : (u32)dn;
+						s.hdr_bytes = hdr;
+						inf_bits_init(s, 0);
+						s.state = ST_HEADER;
+					}
+				}
+			}
+		}
+		if (__all_sync(LDB_FULL_MASK, s.state == ST_IDLE)) {
+			if (__all_sync(LDB_FULL_MASK, exhausted)) break;
+			continue;	// e.g. every fetched chunk had a bad wrapper header
+		}
+
+		// (2) block headers, parsed by their own lanes
+		if (s.state == ST_HEADER) {
+			int v = inf_parse_block_header(s, sm, lane);
+			if (v != LDB_SUCCESS) finish(v);
+		}
+		__syncwarp();
+
+		// (3) stored blocks: warp-wide coalesced copy, one lane's block at a time
+		u32 stored = __ballot_sync(LDB_FULL_MASK, s.state == ST_STORED);
+		while (stored) {
+			u32 owner = __ffs(stored) - 1;
+			stored &= stored - 1;
+			// the owner's partial output word must be in memory first
+			if (lane == owner) inf_flush_partial(s);
+			const u8 *src = (const u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.in + s.in_pos), owner);
+			u8 *dst = (u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.out + s.out_pos), owner);
+			u32 len = __shfl_sync(LDB_FULL_MASK, s.stored_len, owner);
+			for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
+			__syncwarp();
+			if (lane == owner) {
+				s.out_pos += len;
+				// reload the accumulator for the (possibly partial) current word
+				u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
+				s.acc = 0;
+				// bytes of the word that lie before 'out' stay zero and are never stored
+				for (u32 j = 0; j < k; j++) {
+					long pos = (long)s.out_pos - (long)k + (long)j;
+					if (pos >= 0) s.acc |= (u64)(*(volatile u8 *)(s.out + pos)) << (8 * j);
+				}
+				u32 next = s.in_pos + len;
+				if (s.is_final) {
+					// P = 8 * next exactly
+					s.bitbuf = 0; s.bitcnt = 0; s.in_pos = next;
+					finish(LDB_SUCCESS);
+				} else {
+					inf_bits_init(s, next);
+					s.state = ST_HEADER;	// parsed in the next service phase
+				}
+			}
+		}
+
+		// (4) table construction, one lane's tables at a time, whole warp
+		u32 build = __ballot_sync(LDB_FULL_MASK, s.state == ST_BUILD);
+		while (build) {
+			u32 owner = __ffs(build) - 1;
+			build &= build - 1;
+			u32 hlit = __shfl_sync(LDB_FULL_MASK, s.hlit, owner);
+			u32 hdist = __shfl_sync(LDB_FULL_MASK, s.hdist, owner);
+			u32 is_static = __shfl_sync(LDB_FULL_MASK, s.is_static, owner);
+			const u8 *lens = sm + INF_SM_LTAB;
+			u32 ll[9], ol[1];
+#pragma unroll
+			for (int r = 0; r < 9; r++) {
+				u32 sym = r * 32 + lane;
+				ll[r] = is_static ? inf_static_litlen_len(sym)
+						  : (sym < hlit ? lens[byte_idx(sym, owner)] : 0);
+			}
+			ol[0] = is_static ? 5u : (lane < hdist ? lens[byte_idx(hlit + lane, owner)] : 0);
+			__syncwarp();
+			u16 *ovf_owner = (u16 *)a.overflow_scratch + ((size_t)blockIdx.x * 32 + owner) * INF_OVF_ENTRIES;
+			// offset code first, like the reference (decompress_template.h:331-332)
+			bool ok = inf_build_table<1, INF_OB, INF_OSUB_SM, INF_OSUB_CAP, false>(ol, sm, INF_SM_OTAB, ovf_owner + INF_OVF_L, owner, lane);
+			ok = ok && inf_build_table<9, INF_LB, INF_LSUB_SM, INF_LSUB_CAP, true>(ll, sm, INF_SM_LTAB, ovf_owner, owner, lane);
+			__threadfence_block();
+			if (lane == owner) {
+				if (!ok) finish(LDB_BAD_DATA);
+				else s.state = ST_DECODE;
+			}
+		}
+		__syncwarp();
+
+		// ---- decode phase ----------------------------------------------------
+		for (int it = 0; it < INF_QUANTUM; it++) {
+			if (s.state == ST_DECODE) {
+				int v = inf_decode_step(s, sm, ovf, lane);
+				if (v != LDB_SUCCESS) finish(v);
+				else if (s.state == ST_HEADER && s.is_final) finish(LDB_SUCCESS);
+			}
+			if ((it & 31) == 31 && !__any_sync(LDB_FULL_MASK, s.state == ST_DECODE)) break;
+		}
+		__syncwarp();
+	}
+}
+
+// ---- trailer verification (runs after the checksum kernel) ----------------------------
+// ref: lib/gzip_decompress.c:117-127, lib/zlib_decompress.c:82-86
+__global__ void ldb_verify_trailer_kernel(ldb_inflate_args a, const u32 *checksums)
+{
+	size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= a.n) return;
+	if (a.results[c] != LDB_SUCCESS) return;
+	if (checksums[c] != a.trailer_expect[c]) {
+		a.results[c] = LDB_BAD_DATA;
+		return;
+	}
+	if (a.format == LDB_FMT_GZIP && (u32)a.actual_out[c] != a.isize_expect[c])
+		a.results[c] = LDB_BAD_DATA;
+}
+
+int ldb_launch_inflate(const ldb_inflate_args &a, const ldb_launch_cfg &cfg, void *stream)
+{
+	if (a.n == 0) return 0;
+	static bool attr_set = false;
+	if (!attr_set) {
+		LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SM_BYTES));
+		attr_set = true;
+	}
+	u32 *counter = (u32 *)(a.overflow_scratch + (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream());
+	LDB_CUDA_CHECK_RET(cudaMemsetAsync(counter, 0, sizeof(u32), (cudaStream_t)stream));
+	size_t blocks = (a.n + 31) / 32;
+	size_t cap = (size_t)ldb_inflate_grid_blocks(cfg);
+	if (blocks > cap) blocks = cap;
+	LDB_LAUNCH(ldb_inflate_kernel, dim3((unsigned)blocks), dim3(32), INF_SM_BYTES, (cudaStream_t)stream, a, counter);
+	LDB_CUDA_CHECK_RET(cudaGetLastError());
+	return 0;
+}
+
+int ldb_inflate_grid_blocks(const ldb_launch_cfg &cfg)
+{
+	int per_sm = cfg.max_smem_optin / (INF_SM_BYTES + 1024);
+	if (per_sm < 1) per_sm = 1;
+	return cfg.num_sms * per_sm;
+}
+
+size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg)
+{
+	return (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream() + 256;
+}
+
+int ldb_launch_verify_trailer(const ldb_inflate_args &a, const u32 *d_checksums, void *stream)
+{
+	if (a.n == 0) return 0;
+	unsigned blocks = (unsigned)((a.n + 255) / 256);
+	LDB_LAUNCH(ldb_verify_trailer_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, a, d_checksums);
+	LDB_CUDA_CHECK_RET(cudaGetLastError());
+	return 0;
+}

@@ -1,0 +1,123 @@
+"""Parity checks shared by the emulator tests (CPU) and the GPU tests.
+
+Every check drives the SAME C-ABI entry points (`api`/`ctx` wrap either the product
+library on a B200 or the emulator build of the same kernel sources) and compares with
+the oracle (`orc`), with zlib, and -- when it is built -- with the unmodified reference.
+"""
+import random
+import zlib
+
+import corpus
+
+SIZES_CHECKSUM = [0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 64, 255, 256, 511, 512, 513, 1024, 4095, 5552, 5553, 32768, 65536, 262144 + 17]
+
+
+def check_checksums(api, orc, sizes=SIZES_CHECKSUM, seed=3):
+    rng = random.Random(seed)
+    for n in sizes:
+        d = rng.randbytes(n)
+        for init in (0, 0xDEADBEEF):
+            assert api.crc32(d, init) == zlib.crc32(d, init) == orc.crc32(d, init), ("crc32", n, init)
+        for init in (1, (65520 << 16) | 65520):
+            assert api.adler32(d, init) == zlib.adler32(d, init) == orc.adler32(d, init), ("adler32", n, init)
+    # NULL buffer -> initial values (ref: programs/test_checksums.c:63-71)
+    assert api.crc32(None) == 0 and api.adler32(None) == 1
+    # Adler-32 overflow vectors (ref: programs/test_checksums.c:176-196)
+    d = b"\xff" * 5553
+    init = (65520 << 16) | 65520
+    assert api.adler32(d, init) == zlib.adler32(d, init)
+    # multipart continuation (ref: programs/test_checksums.c:74-84)
+    d = rng.randbytes(70000)
+    for cut in (1, 100, 4097, 65535):
+        assert api.crc32(d[cut:], api.crc32(d[:cut])) == zlib.crc32(d)
+        assert api.adler32(d[cut:], api.adler32(d[:cut])) == zlib.adler32(d)
+
+
+def check_checksum_batch(ctx, orc, n_chunks=67, max_len=70000, seed=4):
+    rng = random.Random(seed)
+    bufs = [rng.randbytes(rng.choice([0, 1, 15, 16, 17, 100, 4096, rng.randrange(max_len)])) for _ in range(n_chunks)]
+    assert ctx.checksum_batch_host(bufs, "crc32") == [zlib.crc32(b) for b in bufs]
+    assert ctx.checksum_batch_host(bufs, "adler32") == [zlib.adler32(b) for b in bufs]
+
+
+def make_valid_streams(sizes=(0, 1, 100, 5000, 65536), levels=(1, 6, 9), ref=None):
+    """(format, plain, stream) triples from zlib (independent producer) and, if available,
+    from the reference compressor itself (SURVEY.md section 8c parity definition)."""
+    out = []
+    for n in sizes:
+        for name, plain in corpus.all_classes(n, n + 5).items():
+            for fmt, wb in ((0, -15), (1, 15), (2, 31)):
+                for lv in levels:
+                    out.append((fmt, plain, corpus.zlib_raw(plain, lv, zlib.Z_DEFAULT_STRATEGY, wb)))
+                out.append((fmt, plain, corpus.zlib_raw(plain, 6, zlib.Z_FIXED, wb)))
+                out.append((fmt, plain, corpus.zlib_raw(plain, 0, zlib.Z_DEFAULT_STRATEGY, wb)))
+                if ref is not None:
+                    for lv in (1, 6, 12):
+                        out.append((fmt, plain, ref.compress(plain, lv, fmt)))
+    return out
+
+
+def check_decompress_valid(ctx, orc, streams):
+    for fmt in (0, 1, 2):
+        sel = [s for s in streams if s[0] == fmt]
+        got = ctx.decompress_batch_host([s[2] for s in sel], [len(s[1]) for s in sel], fmt)
+        for (f, plain, z), g in zip(sel, got):
+            o = orc.decompress(z, len(plain), fmt)
+            assert o[0] == 0 and o[1] == plain
+            assert g == o, ("valid stream mismatch", fmt, len(plain), g[0], g[2:], o[2:])
+        # exact-size mode and over-sized buffers
+        got = ctx.decompress_batch_host([s[2] for s in sel], [len(s[1]) for s in sel], fmt, exact=True)
+        assert all(g[0] == 0 and g[1] == s[1] for g, s in zip(got, sel))
+        got = ctx.decompress_batch_host([s[2] for s in sel], [len(s[1]) + 77 for s in sel], fmt, exact=True)
+        assert all(g[0] == (2 if True else 0) for g in got)	# SHORT_OUTPUT
+        got = ctx.decompress_batch_host([s[2] for s in sel], [len(s[1]) + 77 for s in sel], fmt)
+        assert all(g[0] == 0 and g[1] == s[1] for g, s in zip(got, sel))
+
+
+def fuzz_cases(n_cases, seed, max_size=20000):
+    rng = random.Random(seed)
+    base = []
+    for n in (0, 1, 10, 300, 3000, max_size):
+        for name, v in corpus.all_classes(n, n + 1).items():
+            for fmt, wb in ((0, -15), (1, 15), (2, 31)):
+                base.append((fmt, v, corpus.zlib_raw(v, rng.choice([1, 6, 9]),
+                                                     rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY]), wb)))
+    cases = []
+    for _ in range(n_cases):
+        fmt, v, z = rng.choice(base)
+        z = bytearray(z)
+        mode = rng.randrange(6)
+        if mode == 0 and len(z):
+            for _ in range(rng.randint(1, 3)):
+                z[rng.randrange(len(z))] ^= 1 << rng.randrange(8)
+        elif mode == 1:
+            z = z[:rng.randrange(len(z) + 1)]
+        elif mode == 2:
+            z += bytes(rng.randrange(256) for _ in range(rng.randint(1, 20)))
+        elif mode == 3 and len(z):
+            p = rng.randrange(len(z))
+            z[p:p + rng.randint(1, 4)] = bytes(rng.randrange(256) for _ in range(rng.randint(0, 4)))
+        avail = rng.choice([len(v), len(v), len(v) + rng.randint(0, 100), max(0, len(v) - rng.randint(1, 50)),
+                            rng.randint(0, 2 * len(v) + 10)])
+        cases.append((fmt, bytes(z), avail, rng.random() < 0.3))
+    return cases
+
+
+def check_decompress_fuzz(ctx, checker, cases):
+    """checker.decompress() is the oracle (or the reference); verdicts, byte counts and
+    bytes must agree for every mutated stream."""
+    n_by_verdict = {}
+    for fmt in (0, 1, 2):
+        for exact in (False, True):
+            sel = [c for c in cases if c[0] == fmt and c[3] == exact]
+            if not sel:
+                continue
+            got = ctx.decompress_batch_host([c[1] for c in sel], [c[2] for c in sel], fmt, exact)
+            for c, g in zip(sel, got):
+                r = checker.decompress(c[1], c[2], fmt, exact)
+                n_by_verdict[r[0]] = n_by_verdict.get(r[0], 0) + 1
+                if r[0] == 0:
+                    assert g == r, ("fuzz mismatch", fmt, exact, len(c[1]), c[2], g[0], g[2:], r[2:], c[1][:32].hex())
+                else:
+                    assert g[0] == r[0], ("fuzz verdict mismatch", fmt, exact, len(c[1]), c[2], g[0], r[0], c[1][:32].hex())
+    return n_by_verdict
