@@ -67,6 +67,19 @@ LIBDEFLATEAPI void  libdeflate_b200_pinned_free(void *h_ptr);
 LIBDEFLATEAPI int   libdeflate_b200_memcpy_h2d(struct libdeflate_b200_ctx *ctx, void *d_dst, const void *h_src, size_t nbytes);
 LIBDEFLATEAPI int   libdeflate_b200_memcpy_d2h(struct libdeflate_b200_ctx *ctx, void *h_dst, const void *d_src, size_t nbytes);
 
+/* CUDA-event stopwatch on the context's stream: start records an event, stop records a
+ * second one, waits for it and returns the elapsed device time in milliseconds (<0 on error). */
+LIBDEFLATEAPI int    libdeflate_b200_timer_start(struct libdeflate_b200_ctx *ctx);
+LIBDEFLATEAPI double libdeflate_b200_timer_stop_ms(struct libdeflate_b200_ctx *ctx);
+
+/* Per-kernel device time: with profiling on, every kernel launch is bracketed by two
+ * events on the context's stream.  kernel_time_ms() synchronises, then returns the summed
+ * duration (ms) and launch count of one kind since the last reset.
+ * kind: 0 crc32, 1 adler32, 2 inflate, 3 trailer-verify, 4 deflate. */
+LIBDEFLATEAPI void   libdeflate_b200_ctx_set_profiling(struct libdeflate_b200_ctx *ctx, int on);
+LIBDEFLATEAPI double libdeflate_b200_kernel_time_ms(struct libdeflate_b200_ctx *ctx, int kind, uint64_t *n_launches);
+LIBDEFLATEAPI void   libdeflate_b200_kernel_time_reset(struct libdeflate_b200_ctx *ctx);
+
 /* Number of kernels this library has launched on 'ctx' since creation
  * (bench.py reports it as "gpu_launches"). */
 LIBDEFLATEAPI uint64_t libdeflate_b200_launch_count(struct libdeflate_b200_ctx *ctx);

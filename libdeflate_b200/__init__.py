@@ -41,6 +41,8 @@ BATCH_SYMBOLS = [
     "libdeflate_b200_device_malloc", "libdeflate_b200_device_free",
     "libdeflate_b200_pinned_malloc", "libdeflate_b200_pinned_free",
     "libdeflate_b200_memcpy_h2d", "libdeflate_b200_memcpy_d2h", "libdeflate_b200_launch_count",
+    "libdeflate_b200_timer_start", "libdeflate_b200_timer_stop_ms",
+    "libdeflate_b200_ctx_set_profiling", "libdeflate_b200_kernel_time_ms", "libdeflate_b200_kernel_time_reset",
     "libdeflate_b200_decompress_batch", "libdeflate_b200_compress_batch",
     "libdeflate_b200_crc32_batch", "libdeflate_b200_adler32_batch",
     "libdeflate_b200_decompress_batch_host", "libdeflate_b200_compress_batch_host",
@@ -117,6 +119,16 @@ def load_library(path=None):
     lib.libdeflate_b200_memcpy_h2d.argtypes = [P, P, P, S]
     lib.libdeflate_b200_memcpy_d2h.restype = c_int
     lib.libdeflate_b200_memcpy_d2h.argtypes = [P, P, P, S]
+    lib.libdeflate_b200_timer_start.restype = c_int
+    lib.libdeflate_b200_timer_start.argtypes = [P]
+    lib.libdeflate_b200_timer_stop_ms.restype = ctypes.c_double
+    lib.libdeflate_b200_timer_stop_ms.argtypes = [P]
+    lib.libdeflate_b200_ctx_set_profiling.restype = None
+    lib.libdeflate_b200_ctx_set_profiling.argtypes = [P, c_int]
+    lib.libdeflate_b200_kernel_time_ms.restype = ctypes.c_double
+    lib.libdeflate_b200_kernel_time_ms.argtypes = [P, c_int, POINTER(c_uint64)]
+    lib.libdeflate_b200_kernel_time_reset.restype = None
+    lib.libdeflate_b200_kernel_time_reset.argtypes = [P]
     lib.libdeflate_b200_launch_count.restype = c_uint64
     lib.libdeflate_b200_launch_count.argtypes = [P]
     lib.libdeflate_b200_decompress_batch.restype = c_int

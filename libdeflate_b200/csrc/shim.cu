@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/libdeflate.h"
 #include "../../include/libdeflate_b200.h"
@@ -111,6 +112,13 @@ struct ldb_buf {
 	size_t cap = 0;
 };
 
+// kernel kinds for libdeflate_b200_kernel_time_ms()
+enum { LDB_K_CRC32 = 0, LDB_K_ADLER32 = 1, LDB_K_INFLATE = 2, LDB_K_VERIFY = 3, LDB_K_DEFLATE = 4, LDB_KERNEL_KINDS = 5 };
+struct ldb_prof_rec {
+	cudaEvent_t a, b;
+	int kind;
+};
+
 struct libdeflate_b200_ctx {
 	int device;
 	cudaStream_t stream;
@@ -123,6 +131,12 @@ struct libdeflate_b200_ctx {
 	ldb_buf d_params;		// device: pointer/size arrays for host-buffer calls
 	ldb_buf h_pinned;		// pinned host staging
 	u64 launches;
+	cudaEvent_t ev_start, ev_stop;
+	// optional per-kernel stopwatch (libdeflate_b200_ctx_set_profiling)
+	int profiling;
+	std::vector<ldb_prof_rec> *prof;
+	double prof_ms[LDB_KERNEL_KINDS];
+	u64 prof_n[LDB_KERNEL_KINDS];
 };
 
 static int ldb_reserve_dev(ldb_buf &b, size_t n)
@@ -187,6 +201,13 @@ extern "C" struct libdeflate_b200_ctx *libdeflate_b200_ctx_create(int device)
 		delete ctx;
 		return nullptr;
 	}
+	ctx->profiling = 0;
+	ctx->prof = new std::vector<ldb_prof_rec>();
+	for (int k = 0; k < LDB_KERNEL_KINDS; k++) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+	ctx->ev_start = nullptr;
+	ctx->ev_stop = nullptr;
+	cudaEventCreate(&ctx->ev_start);
+	cudaEventCreate(&ctx->ev_stop);
 	ldb_crc_tables *h = new ldb_crc_tables();
 	ldb_build_crc_tables(h);
 	e = cudaMemcpy(ctx->d_crc_tables, h, sizeof(*h), cudaMemcpyHostToDevice);
@@ -207,6 +228,12 @@ extern "C" void libdeflate_b200_ctx_destroy(struct libdeflate_b200_ctx *ctx)
 		cudaStreamSynchronize(ctx->stream);
 		cudaStreamDestroy(ctx->stream);
 	}
+	if (ctx->prof) {
+		for (auto &r : *ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+		delete ctx->prof;
+	}
+	if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+	if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
 	cudaFree(ctx->d_crc_tables);
 	cudaFree(ctx->inflate_scratch.p);
 	cudaFree(ctx->deflate_scratch.p);
@@ -225,6 +252,66 @@ extern "C" int libdeflate_b200_ctx_sync(struct libdeflate_b200_ctx *ctx)
 }
 extern "C" void *libdeflate_b200_ctx_stream(struct libdeflate_b200_ctx *ctx) { return (void *)ctx->stream; }
 extern "C" uint64_t libdeflate_b200_launch_count(struct libdeflate_b200_ctx *ctx) { return ctx->launches; }
+
+// Every kernel launch of the library goes through this wrapper: it counts the launch
+// and, when profiling is on, brackets it with two events on the launching stream.
+template <typename F> static int ldb_timed_launch(libdeflate_b200_ctx *ctx, int kind, F &&launch)
+{
+	ctx->launches++;
+	if (!ctx->profiling) return launch();
+	ldb_prof_rec r;
+	r.kind = kind;
+	if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess)
+		return ldb_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
+	cudaEventRecord(r.a, ctx->stream);
+	int rc = launch();
+	cudaEventRecord(r.b, ctx->stream);
+	ctx->prof->push_back(r);
+	return rc;
+}
+
+extern "C" void libdeflate_b200_ctx_set_profiling(struct libdeflate_b200_ctx *ctx, int on) { ctx->profiling = on; }
+
+// Sum of device time (ms) and number of launches of one kernel kind since the last reset;
+// synchronises the stream.  kind: 0 crc32, 1 adler32, 2 inflate, 3 verify, 4 deflate.
+extern "C" double libdeflate_b200_kernel_time_ms(struct libdeflate_b200_ctx *ctx, int kind, uint64_t *n_launches)
+{
+	cudaStreamSynchronize(ctx->stream);
+	for (auto &r : *ctx->prof) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+			ctx->prof_ms[r.kind] += ms;
+			ctx->prof_n[r.kind]++;
+		}
+		cudaEventDestroy(r.a);
+		cudaEventDestroy(r.b);
+	}
+	ctx->prof->clear();
+	if (kind < 0 || kind >= LDB_KERNEL_KINDS) return -1.0;
+	if (n_launches) *n_launches = ctx->prof_n[kind];
+	return ctx->prof_ms[kind];
+}
+
+extern "C" void libdeflate_b200_kernel_time_reset(struct libdeflate_b200_ctx *ctx)
+{
+	libdeflate_b200_kernel_time_ms(ctx, 0, nullptr);
+	for (int k = 0; k < LDB_KERNEL_KINDS; k++) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
+}
+
+// CUDA-event stopwatch on the context's stream (the stream the kernels are launched on)
+extern "C" int libdeflate_b200_timer_start(struct libdeflate_b200_ctx *ctx)
+{
+	LDB_CUDA_CHECK_RET(cudaEventRecord(ctx->ev_start, ctx->stream));
+	return 0;
+}
+extern "C" double libdeflate_b200_timer_stop_ms(struct libdeflate_b200_ctx *ctx)
+{
+	float ms = -1.0f;
+	if (cudaEventRecord(ctx->ev_stop, ctx->stream) != cudaSuccess) return -1.0;
+	if (cudaEventSynchronize(ctx->ev_stop) != cudaSuccess) return -1.0;
+	if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop) != cudaSuccess) return -1.0;
+	return (double)ms;
+}
 
 extern "C" void *libdeflate_b200_device_malloc(struct libdeflate_b200_ctx *ctx, size_t nbytes)
 {
@@ -272,8 +359,7 @@ extern "C" int libdeflate_b200_crc32_batch(struct libdeflate_b200_ctx *ctx, cons
 					    uint32_t *d_values, size_t n)
 {
 	if (n == 0) return 0;
-	ctx->launches++;
-	return ldb_launch_crc32(ctx->d_crc_tables, d_ptrs, d_nbytes, d_init, d_values, n, ctx->cfg, ctx->stream);
+	return ldb_timed_launch(ctx, LDB_K_CRC32, [&] { return ldb_launch_crc32(ctx->d_crc_tables, d_ptrs, d_nbytes, d_init, d_values, n, ctx->cfg, ctx->stream); });
 }
 
 extern "C" int libdeflate_b200_adler32_batch(struct libdeflate_b200_ctx *ctx, const void *const *d_ptrs,
@@ -281,8 +367,7 @@ extern "C" int libdeflate_b200_adler32_batch(struct libdeflate_b200_ctx *ctx, co
 					      uint32_t *d_values, size_t n)
 {
 	if (n == 0) return 0;
-	ctx->launches++;
-	return ldb_launch_adler32(d_ptrs, d_nbytes, d_init, d_values, n, ctx->cfg, ctx->stream);
+	return ldb_timed_launch(ctx, LDB_K_ADLER32, [&] { return ldb_launch_adler32(d_ptrs, d_nbytes, d_init, d_values, n, ctx->cfg, ctx->stream); });
 }
 
 extern "C" int libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
@@ -322,18 +407,16 @@ extern "C" int libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx,
 	a.n = n;
 	a.format = format;
 	a.flags = flags;
-	ctx->launches++;
-	rc = ldb_launch_inflate(a, ctx->cfg, ctx->stream);
+	rc = ldb_timed_launch(ctx, LDB_K_INFLATE, [&] { return ldb_launch_inflate(a, ctx->cfg, ctx->stream); });
 	if (rc) return rc;
 	if (format != LDB_FMT_RAW) {
 		// checksum of what was produced, then compare with the trailer
-		ctx->launches += 2;
 		if (format == LDB_FMT_GZIP)
-			rc = ldb_launch_crc32(ctx->d_crc_tables, (const void *const *)d_out_ptrs, a.actual_out, nullptr, sums, n, ctx->cfg, ctx->stream);
+			rc = ldb_timed_launch(ctx, LDB_K_CRC32, [&] { return ldb_launch_crc32(ctx->d_crc_tables, (const void *const *)d_out_ptrs, a.actual_out, nullptr, sums, n, ctx->cfg, ctx->stream); });
 		else
-			rc = ldb_launch_adler32((const void *const *)d_out_ptrs, a.actual_out, nullptr, sums, n, ctx->cfg, ctx->stream);
+			rc = ldb_timed_launch(ctx, LDB_K_ADLER32, [&] { return ldb_launch_adler32((const void *const *)d_out_ptrs, a.actual_out, nullptr, sums, n, ctx->cfg, ctx->stream); });
 		if (rc) return rc;
-		rc = ldb_launch_verify_trailer(a, sums, ctx->stream);
+		rc = ldb_timed_launch(ctx, LDB_K_VERIFY, [&] { return ldb_launch_verify_trailer(a, sums, ctx->stream); });
 	}
 	return rc;
 }
@@ -352,13 +435,10 @@ extern "C" int libdeflate_b200_compress_batch(struct libdeflate_b200_ctx *ctx, i
 	rc = ldb_reserve_dev(ctx->tmp, align_up(n * sizeof(u32), 256));
 	if (rc) return rc;
 	u32 *sums = (u32 *)ctx->tmp.p;
-	if (format == LDB_FMT_GZIP) {
-		ctx->launches++;
-		rc = ldb_launch_crc32(ctx->d_crc_tables, d_in_ptrs, d_in_nbytes, nullptr, sums, n, ctx->cfg, ctx->stream);
-	} else if (format == LDB_FMT_ZLIB) {
-		ctx->launches++;
-		rc = ldb_launch_adler32(d_in_ptrs, d_in_nbytes, nullptr, sums, n, ctx->cfg, ctx->stream);
-	}
+	if (format == LDB_FMT_GZIP)
+		rc = ldb_timed_launch(ctx, LDB_K_CRC32, [&] { return ldb_launch_crc32(ctx->d_crc_tables, d_in_ptrs, d_in_nbytes, nullptr, sums, n, ctx->cfg, ctx->stream); });
+	else if (format == LDB_FMT_ZLIB)
+		rc = ldb_timed_launch(ctx, LDB_K_ADLER32, [&] { return ldb_launch_adler32(d_in_ptrs, d_in_nbytes, nullptr, sums, n, ctx->cfg, ctx->stream); });
 	if (rc) return rc;
 	ldb_deflate_args a;
 	a.in_ptrs = d_in_ptrs;
@@ -372,8 +452,7 @@ extern "C" int libdeflate_b200_compress_batch(struct libdeflate_b200_ctx *ctx, i
 	a.n = n;
 	a.format = format;
 	a.level = level;
-	ctx->launches++;
-	return ldb_launch_deflate(a, ctx->cfg, ctx->stream);
+	return ldb_timed_launch(ctx, LDB_K_DEFLATE, [&] { return ldb_launch_deflate(a, ctx->cfg, ctx->stream); });
 }
 
 // ---------------------------------------------------------------------------------

@@ -1,0 +1,151 @@
+"""`-m gpu`: the parity tests proper -- CUDA path (through the C ABI) vs the oracle, zlib
+and the reference-built fixtures, on a real B200."""
+import ctypes
+import glob
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import corpus
+import parity_checks as pc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def test_native_library_is_loaded():
+    import libdeflate_b200 as ldb
+    assert ldb.lib().libdeflate_b200_device_count() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libdeflate_b200.so" in maps and "libdeflate_b200_emu" not in maps
+
+
+def test_checksums_single_call(gpu_api, oracle):
+    pc.check_checksums(gpu_api, oracle)
+
+
+def test_checksums_batch(gpu_ctx, oracle):
+    pc.check_checksum_batch(gpu_ctx, oracle, n_chunks=300, max_len=300000)
+
+
+def test_checksums_every_alignment(gpu_ctx):
+    """ref: programs/test_checksums.c:154-200 -- every start alignment, ragged lengths."""
+    rng = np.random.default_rng(5)
+    blob = rng.integers(0, 256, 70000, dtype=np.uint8).tobytes()
+    bufs = [blob[a:a + ln] for a in range(0, 33) for ln in (0, 1, 31, 32, 33, 1000, 32768 + a)]
+    assert gpu_ctx.checksum_batch_host(bufs, "crc32") == [zlib.crc32(b) for b in bufs]
+    assert gpu_ctx.checksum_batch_host(bufs, "adler32") == [zlib.adler32(b) for b in bufs]
+
+
+def test_decompress_valid_streams(gpu_ctx, oracle):
+    streams = pc.make_valid_streams(sizes=(0, 1, 100, 5000, 65536), levels=(1, 6, 9))
+    pc.check_decompress_valid(gpu_ctx, oracle, streams)
+
+
+def test_decompress_reference_fixture_streams(gpu_ctx, oracle):
+    """Streams produced by the UNMODIFIED reference compressor (committed fixtures)."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_streams.npz"))
+    names = sorted(k[:-2] for k in fx.files if k.endswith("_z"))
+    for fmt in (0, 1, 2):
+        sel = [n for n in names if n.startswith("f%d_" % fmt)]
+        plains = [fx[n + "_p"].tobytes() for n in sel]
+        zs = [fx[n + "_z"].tobytes() for n in sel]
+        got = gpu_ctx.decompress_batch_host(zs, [len(p) for p in plains], fmt)
+        for g, p, z in zip(got, plains, zs):
+            assert g[0] == 0 and g[1] == p and g[2] == len(z)
+
+
+def test_decompress_1mib_chunks(gpu_ctx, oracle):
+    plains = [corpus.text(1 << 20, 3), corpus.mixed(1 << 20, 4), corpus.zeros(1 << 20)]
+    zs = [corpus.zlib_raw(p, 9) for p in plains]
+    got = gpu_ctx.decompress_batch_host(zs, [len(p) for p in plains], 0)
+    for g, p in zip(got, plains):
+        assert g[0] == 0 and g[1] == p
+
+
+def test_decompress_fuzz_verdicts(gpu_ctx, oracle):
+    seen = pc.check_decompress_fuzz(gpu_ctx, oracle, pc.fuzz_cases(6000, seed=77))
+    assert set(seen) == {0, 1, 2, 3}, seen
+
+
+def test_known_answer_fixtures(gpu_ctx, oracle):
+    """ref: programs/test_incomplete_codes.c, test_invalid_streams.c, test_overread.c --
+    hand-assembled streams with expected bytes / verdicts (tests/golden/known_answer.json)."""
+    import json
+    ka = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answer.json")))
+    zs = [bytes.fromhex(k["stream"]) for k in ka]
+    got = gpu_ctx.decompress_batch_host(zs, [k["out_avail"] for k in ka], 0)
+    for k, g in zip(ka, got):
+        assert g[0] == k["result"], k["name"]
+        if k["result"] == 0:
+            assert g[1] == bytes.fromhex(k["output"]), k["name"]
+
+
+def test_single_buffer_api_round_trip(gpu_api, oracle):
+    for n in (0, 1, 54, 55, 56, 1000, 65536, 200000):
+        d = corpus.text(n, n)
+        for fmt in (0, 1, 2):
+            for lvl in (0, 1, 6, 9, 12):
+                z = gpu_api.compress(d, lvl, fmt)
+                assert z is not None
+                assert len(z) <= oracle.l.oracle_compress_bound(fmt, n)
+                r = oracle.decompress(z, n, fmt)
+                assert r[0] == 0 and r[1] == d
+                wb = {0: -15, 1: 15, 2: 31}[fmt]
+                assert zlib.decompress(z, wb) == d
+                g = gpu_api.decompress(z, n, fmt)
+                assert g[0] == 0 and g[1] == d and g[2] == len(z)
+            # output too small => 0 (ref: libdeflate.h:85-88)
+            if n:
+                assert gpu_api.compress(d, 6, fmt, out_avail=4) is None
+
+
+def test_compress_batch_round_trip_and_bound(gpu_ctx, oracle):
+    chunks = []
+    for n in (0, 1, 300, 5000, 65536):
+        chunks += list(corpus.all_classes(n, n + 9).values())
+    for fmt in (0, 1, 2):
+        for lvl in (0, 1, 6, 9, 12):
+            zs = gpu_ctx.compress_batch_host(chunks, lvl, fmt)
+            for c, z in zip(chunks, zs):
+                assert z is not None and len(z) <= oracle.l.oracle_compress_bound(fmt, len(c))
+                r = oracle.decompress(z, len(c), fmt)
+                assert r[0] == 0 and r[1] == c, (fmt, lvl, len(c))
+
+
+def test_full_size_property_round_trip(gpu_ctx):
+    """BASELINE-sized chunks: 4096 x 64 KiB synthetic text, reference streams in,
+    checksum-of-checksums out (size-independent property)."""
+    import bench
+    synth = bench.load_synth()
+    cpub = bench.load_cpub()
+    if cpub is None:
+        pytest.skip("oracle/_ref not prebuilt")
+    n, chunk = 4096, 65536
+    buf = (ctypes.c_uint8 * (n * chunk))()
+    synth.synth_fill(buf, chunk, 0, n, 6, 8)      # robustness mix T/P/S/R/Z/M
+    tc, td, total, streams = bench.cpu_roundtrip(cpub, 2, 6, buf, chunk, n, bench.host_threads(), want_streams=True)
+    comp, stride, sizes = streams
+    raw = bytes(comp)
+    zs = [raw[i * stride:i * stride + sizes[i]] for i in range(n)]
+    got = gpu_ctx.decompress_batch_host(zs, chunk, 2)
+    plain = bytes(buf)
+    for i, g in enumerate(got):
+        assert g[0] == 0 and g[3] == chunk
+        assert zlib.crc32(g[1]) == zlib.crc32(plain[i * chunk:(i + 1) * chunk])
+
+
+def test_reference_test_programs_against_our_library():
+    """Drop-in acceptance: the reference's own programs/test_*.c, compiled UNMODIFIED here
+    against libdeflate_b200.so (oracle/Makefile `reftests`), run on the GPU box."""
+    progs = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "test_*")))
+    if not progs:
+        pytest.skip("oracle/_ref/test_* not prebuilt")
+    for p in progs:
+        if os.path.basename(p) == "test_slow_decompression":
+            continue        # opt-in perf test in the reference as well (INCLUDE_PERF_TESTS)
+        r = subprocess.run([p], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+        assert r.returncode == 0, (p, r.stdout.decode()[-2000:])
