@@ -46,13 +46,22 @@
 // once).  Back-reference reads are window traffic served by L1/L2.
 #include "ldb_common.cuh"
 
+// table geometry (overridable at build time for tuning sweeps, see scripts/build_variants.py)
+#ifndef INF_LB
 #define INF_LB        9			// main litlen table bits
+#endif
 #define INF_LMAIN     (1 << INF_LB)
+#ifndef INF_LSUB_SM
 #define INF_LSUB_SM   128		// litlen subtable entries kept in shared memory
+#endif
 #define INF_LSUB_CAP  1024		// total litlen subtable capacity (rest in global scratch)
+#ifndef INF_OB
 #define INF_OB        6			// main offset table bits
+#endif
 #define INF_OMAIN     (1 << INF_OB)
+#ifndef INF_OSUB_SM
 #define INF_OSUB_SM   64
+#endif
 #define INF_OSUB_CAP  1024
 #define INF_L_ENTRIES (INF_LMAIN + INF_LSUB_SM)		// 640 u16 per lane
 #define INF_O_ENTRIES (INF_OMAIN + INF_OSUB_SM)		// 128 u16 per lane
@@ -62,7 +71,9 @@
 #define INF_OVF_O     (INF_OSUB_CAP - INF_OSUB_SM)	// 960 u16
 #define INF_OVF_ENTRIES (INF_OVF_L + INF_OVF_O)
 
+#ifndef INF_QUANTUM
 #define INF_QUANTUM   192		// decode iterations between service phases
+#endif
 
 // per-warp shared memory layout (bytes)
 #define INF_SM_LTAB    0
@@ -70,8 +81,12 @@
 #define INF_SM_SCRATCH (INF_SM_OTAB + INF_O_WORDS * 32 * 4)	// 49152
 #define INF_SM_CNT     (INF_SM_SCRATCH)				// u32[16]
 #define INF_SM_CODE    (INF_SM_CNT + 64)			// u32[16]
-#define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[512]
-#define INF_SM_BYTES   (INF_SM_SUBBITS + 512)			// 49792
+#define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[1 << INF_LB]
+#define INF_SM_BYTES   (INF_SM_SUBBITS + (1 << INF_LB))		// 49792 with the default geometry
+
+static_assert(INF_L_ENTRIES >= 320, "the litlen region doubles as the 320-entry code-length scratch");
+static_assert(INF_O_ENTRIES >= 128 || INF_L_ENTRIES >= 448, "precode table scratch");
+static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry");
 
 // entry encodings (u16)
 #define LE_LEN_FLAG  0x4000u
@@ -84,171 +99,207 @@ enum { ST_IDLE = 0, ST_HEADER = 1, ST_BUILD = 2, ST_STORED = 3, ST_DECODE = 4 };
 size_t ldb_inflate_overflow_bytes_per_stream(void) { return INF_OVF_ENTRIES * sizeof(u16); }
 
 struct inf_lane {
-	// input
+	// input: the stream is read as 4-byte aligned words; w0/w1 are the two words the
+	// next peek draws from, w2 is one word of lookahead (latency hiding)
 	const u8 *in;		// start of the DEFLATE stream (after any wrapper header)
+	const u8 *in_al;	// 'in' rounded down to a 4-byte boundary
+	u32 in_a0;		// in - in_al
 	u32 in_n;		// bytes of DEFLATE data available
-	u32 in_pos;		// bytes appended to bitbuf so far (may exceed in_n: virtual zeros)
-	u64 bitbuf;
-	u32 bitcnt;
-	u32 next_word;
-	// output
+	u32 in_nal;		// in_a0 + in_n: end of the valid bytes relative to in_al
+	u32 wpos;		// byte offset of w0 relative to in_al (multiple of 4; may pass in_nal: virtual zeros)
+	u32 w0, w1, w2;
+	u32 bitpos;		// bits of w0 already consumed
+	// output: bytes are gathered into aligned 4-byte words
 	u8 *out;
 	u32 out_pos;
 	u32 out_avail;
-	u64 acc;		// bytes of the current aligned output word produced so far
+	u32 acc;		// the cnt (< 4) pending bytes of the current output word
+	u32 cnt;
 	// block state
 	u32 state;
 	u32 is_final;
 	u32 hlit, hdist, is_static;
-	u32 stored_len;
+	u32 stored_len, stored_src;
 	// bookkeeping
 	u32 chunk;		// chunk index
 	u32 hdr_bytes;		// wrapper header size
 };
 
 // ---- lane-interleaved table access ------------------------------------------
-__device__ __forceinline__ u32 tab_idx(u32 entry, u32 lane) { return (((entry >> 1) << 5) + lane) * 2 + (entry & 1); }
-__device__ __forceinline__ u32 byte_idx(u32 i, u32 lane) { return (((i >> 2) << 5) + lane) * 4 + (i & 3); }
+// u16 entry e of lane t lives at u16 index e*32 + t: lanes 2k and 2k+1 share a bank, every
+// other pair of lanes never conflicts.
+__device__ __forceinline__ u32 tab_idx(u32 entry, u32 lane) { return entry * 32 + lane; }
 
 // ---- bit reader ---------------------------------------------------------------
-__device__ __forceinline__ u32 inf_ld_word(const u8 *in, u32 pos, u32 n)
+__device__ __forceinline__ u32 inf_ld_word(const inf_lane &s, u32 pos)
 {
-	if (pos + 4 <= n && pos + 4 >= 4)
-		return *(const u32 *)(in + pos);
+	if (pos + 4 <= s.in_nal)
+		return *(const u32 *)(s.in_al + pos);
 	u32 w = 0;
 	for (u32 i = 0; i < 4; i++)
-		if (pos + i < n && pos + i >= pos) w |= (u32)in[pos + i] << (8 * i);
+		if (pos + i < s.in_nal) w |= (u32)s.in_al[pos + i] << (8 * i);
 	return w;
 }
 
+// start reading at byte 'pos' of the stream
 __device__ __forceinline__ void inf_bits_init(inf_lane &s, u32 pos)
 {
-	s.bitbuf = 0;
-	s.bitcnt = 0;
-	s.in_pos = pos;
-	// byte steps until the load address is 4-byte aligned
-	while ((((uintptr_t)s.in + s.in_pos) & 3) != 0) {
-		u32 b = s.in_pos < s.in_n ? s.in[s.in_pos] : 0;
-		s.bitbuf |= (u64)b << s.bitcnt;
-		s.bitcnt += 8;
-		s.in_pos++;
-	}
-	s.next_word = inf_ld_word(s.in, s.in_pos, s.in_n);
+	u32 abs = s.in_a0 + pos;
+	s.wpos = abs & ~3u;
+	s.bitpos = 8 * (abs & 3);
+	s.w0 = inf_ld_word(s, s.wpos);
+	s.w1 = inf_ld_word(s, s.wpos + 4);
+	s.w2 = inf_ld_word(s, s.wpos + 8);
 }
 
-__device__ __forceinline__ void inf_refill(inf_lane &s)
+// 32 bits of lookahead (bitpos < 32 afterwards)
+__device__ __forceinline__ u32 inf_peek(inf_lane &s)
 {
-	if (s.bitcnt < 32) {
-		s.bitbuf |= (u64)s.next_word << s.bitcnt;
-		s.bitcnt += 32;
-		s.in_pos += 4;
-		s.next_word = inf_ld_word(s.in, s.in_pos, s.in_n);
+	if (s.bitpos >= 32) {
+		s.w0 = s.w1;
+		s.w1 = s.w2;
+		s.wpos += 4;
+		s.bitpos -= 32;
+		s.w2 = inf_ld_word(s, s.wpos + 8);
 	}
+	return __funnelshift_r(s.w0, s.w1, s.bitpos);
 }
 
 __device__ __forceinline__ u32 inf_take(inf_lane &s, u32 nbits)
 {
-	u32 v = (u32)s.bitbuf & ((1u << nbits) - 1);
-	s.bitbuf >>= nbits;
-	s.bitcnt -= nbits;
+	u32 v = inf_peek(s) & ((1u << nbits) - 1);
+	s.bitpos += nbits;
 	return v;
 }
 
-// P = bits consumed so far
-__device__ __forceinline__ u64 inf_bits_consumed(const inf_lane &s) { return (u64)s.in_pos * 8 - s.bitcnt; }
+// P = bits of the stream consumed so far
+__device__ __forceinline__ u64 inf_bits_consumed(const inf_lane &s)
+{
+	return (u64)s.wpos * 8 + s.bitpos - 8 * s.in_a0;
+}
 
 // ---- output -------------------------------------------------------------------
-// acc holds the already produced bytes of the aligned 8-byte word that contains
-// out_pos (zero elsewhere).  A completed word is stored at once.
-__device__ __forceinline__ void inf_store_word(const inf_lane &s, u32 pos_end, u64 w)
+// pos_end = out position just past the word's last byte; the word is 4-byte aligned in
+// memory by construction.  Only the very first word of a chunk can start before 'out'.
+__device__ __forceinline__ void inf_store_word(const inf_lane &s, u32 pos_end, u32 w)
 {
-	// word covers absolute addresses [A, A+8), A+8 == out + pos_end rounded: pos_end is
-	// the out position just past the last byte of the word that is valid.
-	uintptr_t a_end = (uintptr_t)s.out + pos_end;		// one past last valid byte
-	uintptr_t A = (a_end - 1) & ~(uintptr_t)7;
-	if (A >= (uintptr_t)s.out && A + 8 <= (uintptr_t)s.out + s.out_avail) {
-		*(u64 *)A = w;
+	if (pos_end >= 4) {
+		*(u32 *)(s.out + pos_end - 4) = w;
 	} else {
-		uintptr_t lo = A < (uintptr_t)s.out ? (uintptr_t)s.out : A;
-		for (uintptr_t p = lo; p < a_end; p++)
-			*(u8 *)p = (u8)(w >> (8 * (p - A)));
+		for (u32 j = 4 - pos_end; j < 4; j++) s.out[pos_end - 4 + j] = (u8)(w >> (8 * j));
 	}
 }
 
 __device__ __forceinline__ void inf_put_byte(inf_lane &s, u32 b)
 {
-	u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
-	s.acc |= (u64)b << (8 * k);
+	s.acc |= b << (8 * s.cnt);
+	s.cnt++;
 	s.out_pos++;
-	if (k == 7) {
+	if (s.cnt == 4) {
 		inf_store_word(s, s.out_pos, s.acc);
 		s.acc = 0;
+		s.cnt = 0;
 	}
 }
 
-// make the partial word visible in memory (needed before reading it back)
-__device__ __forceinline__ void inf_flush_partial(const inf_lane &s)
+__device__ __forceinline__ void inf_put_word(inf_lane &s, u32 w)
 {
-	u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
-	if (k) inf_store_word(s, s.out_pos, s.acc);
+	u32 sh = 8 * s.cnt;
+	s.out_pos += 4;
+	inf_store_word(s, s.out_pos - s.cnt, s.acc | (w << sh));
+	s.acc = __funnelshift_rc(w, 0, 32 - sh);	// the cnt bytes of w that did not fit
 }
 
-// unaligned 8-byte read of already written output at position pos (pos < out_pos)
-__device__ __forceinline__ u64 inf_read8(const inf_lane &s, u32 pos)
+// r in 1..3 bytes (already masked)
+__device__ __forceinline__ void inf_put_bytes(inf_lane &s, u32 w, u32 r)
 {
-	uintptr_t a = (uintptr_t)s.out + pos;
-	uintptr_t A = a & ~(uintptr_t)7;
-	u32 sh = (u32)(a & 7) * 8;
-	u64 v0 = *(const volatile u64 *)A;
-	if (sh == 0) return v0;
-	u64 v1 = *(const volatile u64 *)(A + 8);
-	return (v0 >> sh) | (v1 << (64 - sh));
+	u32 sh = 8 * s.cnt;
+	u32 lo = s.acc | (w << sh);
+	s.out_pos += r;
+	u32 c = s.cnt + r;
+	if (c >= 4) {
+		c -= 4;
+		inf_store_word(s, s.out_pos - c, lo);
+		s.acc = __funnelshift_rc(w, 0, 32 - sh);
+	} else {
+		s.acc = lo;
+	}
+	s.cnt = c;
+}
+
+// make the pending bytes visible in memory (needed before reading them back)
+__device__ __forceinline__ void inf_flush_pending(const inf_lane &s)
+{
+	for (u32 j = 0; j < s.cnt; j++) {
+		int pos = (int)s.out_pos - (int)s.cnt + (int)j;
+		if (pos >= 0) s.out[pos] = (u8)(s.acc >> (8 * j));
+	}
+}
+
+// after bytes were written behind our back (stored blocks): reload the pending bytes
+__device__ __forceinline__ void inf_reload_pending(inf_lane &s)
+{
+	s.cnt = (u32)((uintptr_t)s.out + s.out_pos) & 3;
+	s.acc = 0;
+	for (u32 j = 0; j < s.cnt; j++) {
+		int pos = (int)s.out_pos - (int)s.cnt + (int)j;
+		if (pos >= 0) s.acc |= (u32)(*(volatile u8 *)(s.out + pos)) << (8 * j);
+	}
 }
 
 __device__ __forceinline__ void inf_copy_match(inf_lane &s, u32 length, u32 offset)
 {
-	u32 remaining = length;
-	if (offset >= 8) {
-		while (remaining) {
-			u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
-			u32 nb = 8 - k;
-			if (nb > remaining) nb = remaining;
-			u64 src = inf_read8(s, s.out_pos - offset);
-			if (nb < 8) src &= ((u64)1 << (8 * nb)) - 1;
-			s.acc |= src << (8 * k);
-			s.out_pos += nb;
-			remaining -= nb;
-			if (k + nb == 8) {
-				inf_store_word(s, s.out_pos, s.acc);
-				s.acc = 0;
-			}
+	if (offset >= 16) {
+		// far source: every source word is complete in memory at least one step ahead of
+		// its use (offset >= 12 + cnt), so the next word is loaded while the current one
+		// is merged and stored
+		const u8 *a = s.out + (s.out_pos - offset);
+		const u32 *A = (const u32 *)((uintptr_t)a & ~(uintptr_t)3);
+		const u32 sh = 8 * ((u32)(uintptr_t)a & 3);
+		u32 lo = A[0], hi = A[1];
+		A += 2;
+		while (length >= 4) {
+			u32 w = __funnelshift_r(lo, hi, sh);
+			lo = hi;
+			if (length > 4) hi = *A++;
+			inf_put_word(s, w);
+			length -= 4;
+		}
+		if (length) inf_put_bytes(s, __funnelshift_r(lo, hi, sh) & ((1u << (8 * length)) - 1), length);
+	} else if (offset >= 8) {
+		// near source: a source word is only complete once the previous output word has
+		// been stored (offset >= 4 + cnt), so load right before use
+		const u8 *a = s.out + (s.out_pos - offset);
+		const u32 *A = (const u32 *)((uintptr_t)a & ~(uintptr_t)3);
+		const u32 sh = 8 * ((u32)(uintptr_t)a & 3);
+		u32 lo = A[0];
+		while (length >= 4) {
+			u32 hi = *(const volatile u32 *)(A + 1);
+			inf_put_word(s, __funnelshift_r(lo, hi, sh));
+			lo = hi;
+			A++;
+			length -= 4;
+		}
+		if (length) {
+			u32 hi = *(const volatile u32 *)(A + 1);
+			inf_put_bytes(s, __funnelshift_r(lo, hi, sh) & ((1u << (8 * length)) - 1), length);
 		}
 	} else {
 		// periodic source: expand the last 'offset' bytes in registers
-		inf_flush_partial(s);
-		u64 cur = inf_read8(s, s.out_pos - offset);
+		inf_flush_pending(s);
+		u64 cur = 0;
+		for (u32 j = 0; j < offset; j++) cur |= (u64)s.out[s.out_pos - offset + j] << (8 * j);
 		u32 ob = 8 * offset;
-		cur &= ((u64)1 << ob) - 1;
 		cur |= cur << ob;
 		if (2 * ob < 64) cur |= cur << (2 * ob);
 		if (4 * ob < 64) cur |= cur << (4 * ob);
-		while (remaining) {
-			u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
-			u32 nb = 8 - k;
-			if (nb > remaining) nb = remaining;
-			u64 src = cur;
-			if (nb < 8) src &= ((u64)1 << (8 * nb)) - 1;
-			s.acc |= src << (8 * k);
-			s.out_pos += nb;
-			remaining -= nb;
-			if (k + nb == 8) {
-				inf_store_word(s, s.out_pos, s.acc);
-				s.acc = 0;
-			}
-			// advance the pattern by nb bytes
-			u32 r = nb % offset;
+		const u32 r = offset == 3 ? 1 : (offset > 4 ? 4 : 0);	// 4 mod offset
+		while (length >= 4) {
+			inf_put_word(s, (u32)cur);
 			if (r) cur = (cur >> (8 * r)) | (cur << (8 * (offset - r)));
+			length -= 4;
 		}
+		if (length) inf_put_bytes(s, (u32)cur & ((1u << (8 * length)) - 1), length);
 	}
 }
 
@@ -302,11 +353,11 @@ __device__ u32 inf_parse_wrapper(const u8 *in, size_t n, int format, u32 *footer
 // to abort the stream.
 __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 {
-	u8 *lens = sm + INF_SM_LTAB;		// byte_idx(i, lane)
-	u8 *pretab = sm + INF_SM_OTAB;		// byte_idx(i, lane), 128 entries
+	// scratch inside the lane's own (about to be rebuilt) table slots: one u16 slot per value
+	u16 *lens = (u16 *)(sm + INF_SM_LTAB);	// tab_idx(i, lane), <= 320 code lengths
+	u16 *pretab = (u16 *)(sm + INF_SM_OTAB);	// tab_idx(i, lane), 128 precode entries
 	static const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-	inf_refill(s);
 	s.is_final = inf_take(s, 1);
 	u32 btype = inf_take(s, 2);
 
@@ -322,7 +373,6 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 		u32 cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 		u64 packed = 0;		// 19 x 3 bits, indexed by symbol
 		for (u32 i = 0; i < hclen; i++) {
-			inf_refill(s);
 			u32 l = inf_take(s, 3);
 			packed |= (u64)l << (3 * perm[i]);
 		}
@@ -343,7 +393,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 				for (int q = 0; q < 19; q++)
 					if (plen[q] == 1) { sym = q; break; }
 			}
-			for (u32 i = 0; i < 128; i++) pretab[byte_idx(i, lane)] = (u8)((sym << 3) | 1);
+			for (u32 i = 0; i < 128; i++) pretab[tab_idx(i, lane)] = (u16)((sym << 3) | 1);
 		} else {
 			u32 code = 0;
 			for (u32 l = 1; l <= maxlen; l++) {
@@ -351,7 +401,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 					if (plen[sym] != l) continue;
 					u32 rev = __brev(code) >> (32 - l);
 					for (u32 i = rev; i < 128; i += 1u << l)
-						pretab[byte_idx(i, lane)] = (u8)((sym << 3) | l);
+						pretab[tab_idx(i, lane)] = (u16)((sym << 3) | l);
 					code++;
 				}
 				code <<= 1;
@@ -363,14 +413,11 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 		u32 i = 0;
 		u32 prev = 0;
 		while (i < total) {
-			inf_refill(s);
-			u32 e = pretab[byte_idx((u32)s.bitbuf & 127, lane)];
-			u32 l = e & 7;
-			s.bitbuf >>= l;
-			s.bitcnt -= l;
+			u32 e = pretab[tab_idx(inf_peek(s) & 127, lane)];
+			s.bitpos += e & 7;
 			u32 presym = e >> 3;
 			if (presym < 16) {
-				lens[byte_idx(i, lane)] = (u8)presym;
+				lens[tab_idx(i, lane)] = (u16)presym;
 				prev = presym;
 				i++;
 				continue;
@@ -389,7 +436,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 			}
 			// running past the announced count is an error (decompress_template.h:245)
 			if (i + rep > total) return LDB_BAD_DATA;
-			for (u32 k = 0; k < rep; k++) lens[byte_idx(i + k, lane)] = (u8)val;
+			for (u32 k = 0; k < rep; k++) lens[tab_idx(i + k, lane)] = (u16)val;
 			prev = val;
 			i += rep;
 		}
@@ -409,7 +456,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 		if (len != (nlen ^ 0xffffu)) return LDB_BAD_DATA;
 		if (len > s.out_avail - s.out_pos) return LDB_INSUFFICIENT_SPACE;
 		if (len > s.in_n - (B + 4)) return LDB_BAD_DATA;
-		s.in_pos = B + 4;	// source position of the raw bytes
+		s.stored_src = B + 4;	// source position of the raw bytes
 		s.stored_len = len;
 		s.state = ST_STORED;
 		return LDB_SUCCESS;
@@ -608,24 +655,24 @@ __device__ __forceinline__ int inf_decode_step(inf_lane &s, const u8 *sm, const 
 	const u16 *ltab = (const u16 *)(sm + INF_SM_LTAB);
 	const u16 *otab = (const u16 *)(sm + INF_SM_OTAB);
 
-	inf_refill(s);
-	if (s.in_pos > s.in_n) {
-		// virtual zero bytes are in play: P >= 8n+9 means the reference's refill
+	u32 bits = inf_peek(s);
+	if (s.wpos + 8 > s.in_nal) {
+		// virtual zero bytes are (nearly) in play: P >= 8n+9 means the reference's refill
 		// over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
 		if (inf_bits_consumed(s) >= (u64)s.in_n * 8 + 9) return LDB_BAD_DATA;
 	}
-	u32 e = ltab[tab_idx((u32)s.bitbuf & (INF_LMAIN - 1), lane)];
+	u32 e = ltab[tab_idx(bits & (INF_LMAIN - 1), lane)];
 	if (e >= LE_SUB_FLAG) {
 		u32 sstart = (e >> 4) & 0x3ff;
 		u32 sb = e & 15;
-		s.bitbuf >>= INF_LB;
-		s.bitcnt -= INF_LB;
-		u32 idx = sstart + ((u32)s.bitbuf & ((1u << sb) - 1));
+		bits >>= INF_LB;
+		s.bitpos += INF_LB;
+		u32 idx = sstart + (bits & ((1u << sb) - 1));
 		e = idx < INF_LSUB_SM ? ltab[tab_idx(INF_LMAIN + idx, lane)] : ovf[idx - INF_LSUB_SM];
 	}
 	u32 cl = e & 15;
-	s.bitbuf >>= cl;
-	s.bitcnt -= cl;
+	bits >>= cl;
+	s.bitpos += cl;
 	if (e < 0x1000) {
 		if (s.out_pos == s.out_avail) return LDB_INSUFFICIENT_SPACE;
 		inf_put_byte(s, e >> 4);
@@ -635,43 +682,41 @@ __device__ __forceinline__ int inf_decode_step(inf_lane &s, const u8 *sm, const 
 		s.state = ST_HEADER;	// caller turns this into "done" when is_final
 		return LDB_SUCCESS;
 	}
-	// length (Appendix A table, ref: deflate_decompress.c:576-587)
+	// length (Appendix A table, ref: deflate_decompress.c:576-587); 'bits' still holds >= 12 bits
 	u32 slot = (e >> 4) & 31;
 	u32 length;
 	if (slot < 8) {
 		length = 3 + slot;
 	} else if (slot < 28) {
 		u32 eb = (slot - 4) >> 2;
-		length = 3 + ((4 + (slot & 3)) << eb) + ((u32)s.bitbuf & ((1u << eb) - 1));
-		s.bitbuf >>= eb;
-		s.bitcnt -= eb;
+		length = 3 + ((4 + (slot & 3)) << eb) + (bits & ((1u << eb) - 1));
+		s.bitpos += eb;
 	} else {
 		length = 258;
 	}
 	if (length > s.out_avail - s.out_pos) return LDB_INSUFFICIENT_SPACE;
 
-	inf_refill(s);
-	u32 oe = otab[tab_idx((u32)s.bitbuf & (INF_OMAIN - 1), lane)];
+	bits = inf_peek(s);
+	u32 oe = otab[tab_idx(bits & (INF_OMAIN - 1), lane)];
 	if (oe & OE_SUB_FLAG) {
 		u32 sstart = (oe >> 4) & 0x3ff;
 		u32 sb = oe & 15;
-		s.bitbuf >>= INF_OB;
-		s.bitcnt -= INF_OB;
-		u32 idx = sstart + ((u32)s.bitbuf & ((1u << sb) - 1));
+		bits >>= INF_OB;
+		s.bitpos += INF_OB;
+		u32 idx = sstart + (bits & ((1u << sb) - 1));
 		oe = idx < INF_OSUB_SM ? otab[tab_idx(INF_OMAIN + idx, lane)] : ovf[INF_OVF_L + idx - INF_OSUB_SM];
 	}
 	u32 ocl = oe & 15;
-	s.bitbuf >>= ocl;
-	s.bitcnt -= ocl;
+	bits >>= ocl;
+	s.bitpos += ocl;
 	u32 oslot = (oe >> 4) & 31;
 	u32 offset;
 	if (oslot < 4) {
 		offset = 1 + oslot;
 	} else {
 		u32 eb = (oslot - 2) >> 1;
-		offset = 1 + ((2 + (oslot & 1)) << eb) + ((u32)s.bitbuf & ((1u << eb) - 1));
-		s.bitbuf >>= eb;
-		s.bitcnt -= eb;
+		offset = 1 + ((2 + (oslot & 1)) << eb) + (bits & ((1u << eb) - 1));
+		s.bitpos += eb;
 	}
 	if (offset > s.out_pos) return LDB_BAD_DATA;
 	inf_copy_match(s, length, offset);
@@ -689,9 +734,9 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 	inf_lane s;
 	s.state = ST_IDLE;
 	s.chunk = 0xffffffffu;
-	s.in = nullptr; s.in_n = 0; s.in_pos = 0; s.bitbuf = 0; s.bitcnt = 0; s.next_word = 0;
-	s.out = nullptr; s.out_pos = 0; s.out_avail = 0; s.acc = 0;
-	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.hdr_bytes = 0;
+	s.in = nullptr; s.in_al = nullptr; s.in_a0 = 0; s.in_n = 0; s.in_nal = 0; s.wpos = 0; s.w0 = 0; s.w1 = 0; s.w2 = 0; s.bitpos = 0;
+	s.out = nullptr; s.out_pos = 0; s.out_avail = 0; s.acc = 0; s.cnt = 0;
+	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0;
 	bool exhausted = false;
 
 	// finishes the lane's stream with 'verdict' and makes the lane idle
@@ -699,9 +744,7 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 		const size_t c = s.chunk;
 		u32 footer = a.format == LDB_FMT_GZIP ? 8 : (a.format == LDB_FMT_ZLIB ? 4 : 0);
 		if (verdict == LDB_SUCCESS) {
-			// flush the partial output word
-			u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
-			if (k) inf_store_word(s, s.out_pos, s.acc);
+			inf_flush_pending(s);
 			u64 P = inf_bits_consumed(s);
 			if (P > (u64)s.in_n * 8) verdict = LDB_BAD_DATA;	// decompress_template.h:754
 			else {
@@ -746,6 +789,7 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 					s.out_avail = oa > 0xfffffff0u ? 0xfffffff0u : (u32)oa;
 					s.out_pos = 0;
 					s.acc = 0;
+					s.cnt = (u32)(uintptr_t)s.out & 3;	// the first word may start before 'out'
 					u32 footer;
 					u32 hdr = inf_parse_wrapper(in, n, a.format, &footer);
 					if (hdr == 0xffffffffu) {
@@ -755,6 +799,9 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 						size_t dn = n - hdr - footer;
 						s.in = in + hdr;
 						s.in_n = dn > 0xfffffff0u ? 0xfffffff0u : (u32)dn;
+						s.in_a0 = (u32)(uintptr_t)s.in & 3;
+						s.in_al = s.in - s.in_a0;
+						s.in_nal = s.in_a0 + s.in_n;
 						s.hdr_bytes = hdr;
 						inf_bits_init(s, 0);
 						s.state = ST_HEADER;
@@ -779,32 +826,20 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 		while (stored) {
 			u32 owner = __ffs(stored) - 1;
 			stored &= stored - 1;
-			// the owner's partial output word must be in memory first
-			if (lane == owner) inf_flush_partial(s);
-			const u8 *src = (const u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.in + s.in_pos), owner);
+			// the owner's pending output bytes must be in memory first
+			if (lane == owner) inf_flush_pending(s);
+			const u8 *src = (const u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.in + s.stored_src), owner);
 			u8 *dst = (u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.out + s.out_pos), owner);
 			u32 len = __shfl_sync(LDB_FULL_MASK, s.stored_len, owner);
 			for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
 			__syncwarp();
 			if (lane == owner) {
 				s.out_pos += len;
-				// reload the accumulator for the (possibly partial) current word
-				u32 k = (u32)((uintptr_t)s.out + s.out_pos) & 7;
-				s.acc = 0;
-				// bytes of the word that lie before 'out' stay zero and are never stored
-				for (u32 j = 0; j < k; j++) {
-					long pos = (long)s.out_pos - (long)k + (long)j;
-					if (pos >= 0) s.acc |= (u64)(*(volatile u8 *)(s.out + pos)) << (8 * j);
-				}
-				u32 next = s.in_pos + len;
-				if (s.is_final) {
-					// P = 8 * next exactly
-					s.bitbuf = 0; s.bitcnt = 0; s.in_pos = next;
-					finish(LDB_SUCCESS);
-				} else {
-					inf_bits_init(s, next);
-					s.state = ST_HEADER;	// parsed in the next service phase
-				}
+				inf_reload_pending(s);
+				u32 next = s.stored_src + len;
+				inf_bits_init(s, next);	// P = 8 * next exactly
+				if (s.is_final) finish(LDB_SUCCESS);
+				else s.state = ST_HEADER;	// parsed in the next service phase
 			}
 		}
 
@@ -816,15 +851,15 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 			u32 hlit = __shfl_sync(LDB_FULL_MASK, s.hlit, owner);
 			u32 hdist = __shfl_sync(LDB_FULL_MASK, s.hdist, owner);
 			u32 is_static = __shfl_sync(LDB_FULL_MASK, s.is_static, owner);
-			const u8 *lens = sm + INF_SM_LTAB;
+			const u16 *lens = (const u16 *)(sm + INF_SM_LTAB);
 			u32 ll[9], ol[1];
 #pragma unroll
 			for (int r = 0; r < 9; r++) {
 				u32 sym = r * 32 + lane;
 				ll[r] = is_static ? inf_static_litlen_len(sym)
-						  : (sym < hlit ? lens[byte_idx(sym, owner)] : 0);
+						  : (sym < hlit ? lens[tab_idx(sym, owner)] : 0);
 			}
-			ol[0] = is_static ? 5u : (lane < hdist ? lens[byte_idx(hlit + lane, owner)] : 0);
+			ol[0] = is_static ? 5u : (lane < hdist ? lens[tab_idx(hlit + lane, owner)] : 0);
 			__syncwarp();
 			u16 *ovf_owner = (u16 *)a.overflow_scratch + ((size_t)blockIdx.x * 32 + owner) * INF_OVF_ENTRIES;
 			// offset code first, like the reference (decompress_template.h:331-332)

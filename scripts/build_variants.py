@@ -1,0 +1,36 @@
+"""Tuning sweeps: builds variant libraries (different -D geometry) under build/variants/.
+Dev tooling only; the product library is always libdeflate_b200/libdeflate_b200.so."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libdeflate_b200 import build as b  # noqa: E402
+
+VARIANTS = {
+    "lb9": [],
+    "lb8": ["-DINF_LB=8", "-DINF_LSUB_SM=128", "-DINF_OB=6", "-DINF_OSUB_SM=64"],
+    "lb8s": ["-DINF_LB=8", "-DINF_LSUB_SM=64", "-DINF_OB=6", "-DINF_OSUB_SM=64"],
+    "lb7": ["-DINF_LB=7", "-DINF_LSUB_SM=192", "-DINF_OB=6", "-DINF_OSUB_SM=64"],
+    "lb10": ["-DINF_LB=10", "-DINF_LSUB_SM=64", "-DINF_OB=7", "-DINF_OSUB_SM=64"],
+}
+
+
+def main():
+    outdir = os.path.join(ROOT, "build", "variants")
+    os.makedirs(outdir, exist_ok=True)
+    nvcc = "/usr/local/cuda/bin/nvcc"
+    for name, defs in VARIANTS.items():
+        objs = []
+        for src in b.SOURCES:
+            obj = os.path.join(outdir, "%s_%s.o" % (name, src.replace(".cu", "")))
+            subprocess.check_call([nvcc] + [f for f in b.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + defs + ["-c", os.path.join(b.CSRC, src), "-o", obj])
+            objs.append(obj)
+        so = os.path.join(outdir, "libdeflate_b200_%s.so" % name)
+        subprocess.check_call([nvcc, "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static"])
+        print(so)
+
+
+if __name__ == "__main__":
+    main()

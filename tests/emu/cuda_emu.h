@@ -36,7 +36,6 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
-#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __constant__ static
 #define __shared__ static thread_local

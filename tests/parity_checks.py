@@ -121,3 +121,32 @@ def check_decompress_fuzz(ctx, checker, cases):
                 else:
                     assert g[0] == r[0], ("fuzz verdict mismatch", fmt, exact, len(c[1]), c[2], g[0], r[0], c[1][:32].hex())
     return n_by_verdict
+
+
+def check_compress_round_trip(ctx, orc, chunks, levels=(1, 6, 9), fmts=(0, 1, 2), ref=None, max_ratio_vs_ref=None):
+    """Compressed bytes are not contractual (libdeflate.h:76-83); what is: the stream inflates
+    back to the input with the oracle AND zlib, it fits *_compress_bound(), an exactly sized
+    output buffer works and one byte less returns 0."""
+    wbits = {0: -15, 1: 15, 2: 31}
+    stats = []
+    for fmt in fmts:
+        for lvl in levels:
+            zs = ctx.compress_batch_host(chunks, lvl, fmt)
+            for c, z in zip(chunks, zs):
+                assert z is not None, ("did not fit its bound", fmt, lvl, len(c))
+                assert len(z) <= orc.l.oracle_compress_bound(fmt, len(c)), (fmt, lvl, len(c), len(z))
+                r = orc.decompress(z, len(c), fmt)
+                assert r[0] == 0 and r[1] == c and r[2] == len(z), ("oracle cannot inflate it", fmt, lvl, len(c))
+                assert zlib.decompress(z, wbits[fmt]) == c
+                if ref is not None:
+                    stats.append((lvl, len(c), len(z), len(ref.compress(c, lvl, fmt))))
+            # exact fit and one-byte-short (same streams are deterministic)
+            exact = [ctx.compress_batch_host([c], lvl, fmt, out_avail=len(z))[0] for c, z in list(zip(chunks, zs))[:3]]
+            assert all(e == z for e, z in zip(exact, zs)), ("exact-size buffer failed", fmt, lvl)
+            short = [ctx.compress_batch_host([c], lvl, fmt, out_avail=len(z) - 1)[0] for c, z in list(zip(chunks, zs))[:3]]
+            assert all(s is None for s in short), ("short buffer did not return 0", fmt, lvl)
+    if ref is not None and max_ratio_vs_ref is not None:
+        ours = sum(s[2] for s in stats)
+        theirs = sum(s[3] for s in stats)
+        assert ours <= theirs * max_ratio_vs_ref, ("ratio regression", ours, theirs)
+    return stats

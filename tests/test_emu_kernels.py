@@ -22,3 +22,25 @@ def test_inflate_valid_streams_emulated(emu_ctx, oracle, reflib):
 def test_inflate_fuzz_emulated(emu_ctx, oracle):
     v = pc.check_decompress_fuzz(emu_ctx, oracle, pc.fuzz_cases(1500, seed=11))
     assert set(v) >= {0, 1, 3}, v
+
+
+def test_deflate_round_trip_emulated(emu_ctx, oracle, reflib):
+    import corpus
+    chunks = [b"", b"a", corpus.text(56, 1), corpus.text(3000, 2), corpus.pattern(9000), corpus.rand(6000, 3),
+              corpus.zeros(70000), corpus.mixed(40000, 4), corpus.text(65536, 5), corpus.text(100000, 6)]
+    pc.check_compress_round_trip(emu_ctx, oracle, chunks, levels=(0, 1, 6, 12), fmts=(0, 2), ref=reflib, max_ratio_vs_ref=1.10)
+    pc.check_compress_round_trip(emu_ctx, oracle, chunks[:6], levels=(3, 9), fmts=(1,))
+
+
+def test_inflate_output_primitives_unit():
+    """Randomized unit test of the word-accumulator / match-copy primitives (host build)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "emu", "_build", "copy_unit")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DLDB_EMU", "-I", os.path.join(root, "tests", "emu"), "-include", "cuda_emu.h",
+                           "-I", os.path.join(root, "libdeflate_b200", "csrc"), "-fno-strict-aliasing", "-Wno-unused-function", "-w",
+                           os.path.join(root, "tests", "emu", "copy_unit.cpp"), os.path.join(root, "tests", "emu", "cuda_emu.cpp"),
+                           "-o", exe, "-lpthread"])
+    assert subprocess.run([exe]).returncode == 0
