@@ -302,6 +302,32 @@ __device__ __forceinline__ void lz_gen_codes_serial(const u8 *lens, u32 nsyms, u
 	}
 }
 
+// ---- ordered hash-chain insertion of one batch, executed by ONE warp ------------------------
+// For every position p of the batch: next[p] = most recent earlier position with the same
+// 4-byte hash, head[hash] = p (ref semantics: hc_matchfinder.h:227-232).  Same-hash lanes of a
+// 32-position tile are resolved with __match_any_sync; the tile's reads of head[] happen before
+// its writes (two phases).
+__device__ __forceinline__ void lz_insert_batch(const u8 *ring, u16 *head, u16 *nextt, u32 b0, u32 n, u32 lane)
+{
+	const u32 lt = (1u << lane) - 1;
+	for (u32 t = 0; t < LZ_NWIN; t++) {
+		const u32 p = b0 + t * 32 + lane;
+		const bool valid = p + 4 <= n;
+		const u32 h = valid ? lz_hash(lz_ld32(ring, p)) : 0;
+		const u32 m = __match_any_sync(LDB_FULL_MASK, valid ? h : (0x10000u | lane));
+		const u32 old_head = valid ? head[h] : 0;
+		__syncwarp();
+		if (valid) {
+			const u32 below = m & lt;
+			const u32 pred = below ? (p - lane + (31 - __clz(below))) & 0xffff : old_head;
+			nextt[p & (LZ_WIN - 1)] = (u16)pred;
+			if ((m >> lane) == 1) head[h] = (u16)p;	// highest lane of the group
+		}
+		__syncwarp();
+		if (b0 + t * 32 + 32 >= n) break;
+	}
+}
+
 // ---- the kernel ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 ldb_deflate_lz_kernel(ldb_deflate_args a)
@@ -417,77 +443,85 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 
 		for (u32 b0 = 0; b0 < n; b0 += LZ_BATCH) {
 			const u32 bend = b0 + LZ_BATCH < n ? b0 + LZ_BATCH : n;
-			// (a) window staging: the ring must hold [b0 - 32768, bend + 258 + 4)
-			while (loaded_end < n && loaded_end < bend + 512) {
+			// (a) window staging: searching batch b needs [b0 - 32768, bend + 258 + 4); inserting
+			// batch b+1 (which overlaps the search, see below) needs up to b0 + 2*BATCH + 3
+			while (loaded_end < n && loaded_end < b0 + 2 * LZ_BATCH + 512) {
 				u32 to = loaded_end + LZ_SEG < n ? loaded_end + LZ_SEG : n;
 				lz_load_segment(sm, v, in, loaded_end, to);
 				loaded_end = to;
 			}
-			// (b) hashes of the batch positions (all threads) -> rlen[] used as scratch
-			for (u32 i = tid; i < LZ_BATCH; i += LZ_THREADS) {
-				u32 p = b0 + i;
-				rlen[i] = (p + 4 <= n) ? (u16)lz_hash(lz_ld32(ring, p)) : 0xffff;
+			if (b0 == 0) {
+				if (warp == 0) lz_insert_batch(ring, head, nextt, 0, n, lane);
+				__syncthreads();
 			}
-			__syncthreads();
-			// (c) ordered chain insertion by warp 0 (ref semantics: hc_matchfinder.h:227-232)
+			// (b) warp 0 inserts the NEXT batch into the hash chains (ordered, ref semantics:
+			// hc_matchfinder.h:227-232) while the other 15 warps search THIS batch.  Searches
+			// only follow next[] links that point backwards, so later insertions cannot mislead
+			// them (a clobbered link at the far edge of the window fails the monotonic check).
 			if (warp == 0) {
-				const u32 lt = (1u << lane) - 1;
-				for (u32 t = 0; t < LZ_NWIN; t++) {
-					u32 i = t * 32 + lane;
-					u32 p = b0 + i;
-					u32 h = rlen[i];
-					bool valid = h != 0xffff;
-					u32 m = __match_any_sync(LDB_FULL_MASK, valid ? h : (0x10000u | lane));
-					// read phase, then write phase: the group's lowest lane must see the head as it
-					// was BEFORE this tile, the highest lane replaces it
-					u32 old_head = valid ? head[h] : 0;
-					__syncwarp();
-					if (valid) {
-						u32 below = m & lt;
-						u32 pred = below ? (p - lane + (31 - __clz(below))) & 0xffff : old_head;
-						nextt[p & (LZ_WIN - 1)] = (u16)pred;
-						if ((m >> lane) == 1) head[h] = (u16)p;	// highest lane of the group
-					}
-					__syncwarp();
-				}
-			}
-			__syncthreads();
-			// (d) search every position of the batch
-			for (u32 i = tid; i < LZ_BATCH; i += LZ_THREADS) {
-				u32 p = b0 + i;
-				u32 best_len = 0, best_dist = 0;
-				if (p + 4 <= n) {
-					u32 max_len = n - p < 258 ? n - p : 258;
-					u32 nice = (u32)P.nice < max_len ? (u32)P.nice : max_len;
-					u32 cur = lz_ld32(ring, p);
-					u32 cand = nextt[p & (LZ_WIN - 1)];
-					u32 prev_dist = 0;
-					for (int d = 0; d < P.depth; d++) {
-						u32 dist = (p - cand) & 0xffff;
-						if (dist == 0 || dist > LZ_WIN || dist > p || dist <= prev_dist) break;
-						u32 cp = p - dist;
-						if (lz_ld32(ring, cp) == cur &&
-						    (best_len < 4 || lz_ld8(ring, cp + best_len) == lz_ld8(ring, p + best_len))) {
-							u32 len = 4;
-							while (len + 4 <= max_len) {
-								u32 x = lz_ld32(ring, p + len) ^ lz_ld32(ring, cp + len);
-								if (x) { len += (__ffs(x) - 1) >> 3; goto extended; }
-								len += 4;
-							}
-							while (len < max_len && lz_ld8(ring, p + len) == lz_ld8(ring, cp + len)) len++;
-						extended:
-							if (len > best_len) {
-								best_len = len;
-								best_dist = dist;
-								if (len >= nice) break;
+				if (b0 + LZ_BATCH < n) lz_insert_batch(ring, head, nextt, b0 + LZ_BATCH, n, lane);
+			} else {
+				// each searcher owns a run of consecutive positions and carries the match of
+				// position p over to p+1 (same distance, one byte shorter): long matches are
+				// extended once, and the prefilter rejects most chain candidates cheaply
+				const u32 st = tid - 32;
+				const u32 i_begin = (st * LZ_BATCH) / (LZ_THREADS - 32);
+				const u32 i_end = ((st + 1) * LZ_BATCH) / (LZ_THREADS - 32);
+				u32 inh_len = 0, inh_dist = 0;
+				for (u32 i = i_begin; i < i_end; i++) {
+					const u32 p = b0 + i;
+					u32 best_len = inh_len, best_dist = inh_dist;
+					if (p + 4 <= n) {
+						const u32 max_len = n - p < 258 ? n - p : 258;
+						const u32 nice = (u32)P.nice < max_len ? (u32)P.nice : max_len;
+						// the carried-over match may continue past where its predecessor was capped
+						if (best_len)
+							while (best_len < max_len && lz_ld8(ring, p + best_len) == lz_ld8(ring, p - best_dist + best_len)) best_len++;
+						if (best_len < nice) {
+							const u32 cur = lz_ld32(ring, p);
+							u32 tailv = best_len >= 4 ? lz_ld32(ring, p + best_len - 3) : cur;
+							u32 tailo = best_len >= 4 ? best_len - 3 : 0;
+							// candidates older than this have had their next[] slot reused by the batch
+							// being inserted concurrently: end of chain (keeps the output deterministic)
+							const u32 wnd = LZ_WIN - 2 * LZ_BATCH + i;
+							const u32 lim = p < wnd ? p : wnd;
+							u32 cand = nextt[p & (LZ_WIN - 1)];
+							u32 prev_dist = 0;
+							for (int d = 0; d < P.depth; d++) {
+								const u32 dist = (p - cand) & 0xffff;
+								if (dist - 1 >= lim || dist <= prev_dist) break;
+								const u32 cp = p - dist;
+								prev_dist = dist;
+								cand = nextt[cp & (LZ_WIN - 1)];
+								// a longer match must agree on the last 4 bytes of the current best
+								// (ref: hc_matchfinder.h:301-304) and on the first 4
+								if (lz_ld32(ring, cp + tailo) != tailv) continue;
+								if (tailo && lz_ld32(ring, cp) != cur) continue;
+								u32 len = 4;
+								while (len + 4 <= max_len) {
+									u32 x = lz_ld32(ring, p + len) ^ lz_ld32(ring, cp + len);
+									if (x) { len += (__ffs(x) - 1) >> 3; goto extended; }
+									len += 4;
+								}
+								while (len < max_len && lz_ld8(ring, p + len) == lz_ld8(ring, cp + len)) len++;
+							extended:
+								if (len > best_len) {
+									best_len = len;
+									best_dist = dist;
+									if (len >= nice) break;
+									tailo = len - 3;
+									tailv = lz_ld32(ring, p + tailo);
+								}
 							}
 						}
-						prev_dist = dist;
-						cand = nextt[cp & (LZ_WIN - 1)];
+					} else {
+						best_len = 0;
 					}
+					rlen[i] = (u16)best_len;
+					roff[i] = (u16)(best_len ? best_dist - 1 : 0);
+					inh_len = best_len >= 5 ? best_len - 1 : 0;
+					inh_dist = best_dist;
 				}
-				rlen[i] = (u16)best_len;	// rlen held the hashes; they are dead now
-				roff[i] = (u16)(best_len ? best_dist - 1 : 0);
 			}
 			__syncthreads();
 			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping

@@ -48,11 +48,11 @@
 
 // table geometry (overridable at build time for tuning sweeps, see scripts/build_variants.py)
 #ifndef INF_LB
-#define INF_LB        9			// main litlen table bits
+#define INF_LB        8			// main litlen table bits
 #endif
 #define INF_LMAIN     (1 << INF_LB)
 #ifndef INF_LSUB_SM
-#define INF_LSUB_SM   128		// litlen subtable entries kept in shared memory
+#define INF_LSUB_SM   64		// litlen subtable entries kept in shared memory
 #endif
 #define INF_LSUB_CAP  1024		// total litlen subtable capacity (rest in global scratch)
 #ifndef INF_OB
@@ -84,8 +84,8 @@
 #define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[1 << INF_LB]
 #define INF_SM_BYTES   (INF_SM_SUBBITS + (1 << INF_LB))		// 49792 with the default geometry
 
-static_assert(INF_L_ENTRIES >= 320, "the litlen region doubles as the 320-entry code-length scratch");
-static_assert(INF_O_ENTRIES >= 128 || INF_L_ENTRIES >= 448, "precode table scratch");
+static_assert(INF_L_ENTRIES >= 160, "the litlen region doubles as the 320-byte code-length scratch");
+static_assert(INF_O_ENTRIES >= 64, "the offset region doubles as the 128-byte precode table scratch");
 static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry");
 
 // entry encodings (u16)
@@ -120,6 +120,7 @@ struct inf_lane {
 	u32 is_final;
 	u32 hlit, hdist, is_static;
 	u32 stored_len, stored_src;
+	u32 copy_rem, copy_off;	// match bytes still to be copied (continued across iterations)
 	// bookkeeping
 	u32 chunk;		// chunk index
 	u32 hdr_bytes;		// wrapper header size
@@ -129,6 +130,8 @@ struct inf_lane {
 // u16 entry e of lane t lives at u16 index e*32 + t: lanes 2k and 2k+1 share a bank, every
 // other pair of lanes never conflicts.
 __device__ __forceinline__ u32 tab_idx(u32 entry, u32 lane) { return entry * 32 + lane; }
+// byte i of a lane's scratch: low/high byte of the lane's u16 slot i/2
+__device__ __forceinline__ u32 scr_idx(u32 i, u32 lane) { return ((i >> 1) * 32 + lane) * 2 + (i & 1); }
 
 // ---- bit reader ---------------------------------------------------------------
 __device__ __forceinline__ u32 inf_ld_word(const inf_lane &s, u32 pos)
@@ -247,25 +250,33 @@ __device__ __forceinline__ void inf_reload_pending(inf_lane &s)
 	}
 }
 
-__device__ __forceinline__ void inf_copy_match(inf_lane &s, u32 length, u32 offset)
+// Copies 'length' (<= INF_COPY_CHUNK) bytes of a match.  Long matches are continued by the
+// caller in later iterations so that one long match does not stall the other 31 lanes.
+#define INF_COPY_CHUNK 16
+__device__ __forceinline__ void inf_copy_chunk(inf_lane &s, u32 length, u32 offset)
 {
-	if (offset >= 16) {
-		// far source: every source word is complete in memory at least one step ahead of
-		// its use (offset >= 12 + cnt), so the next word is loaded while the current one
-		// is merged and stored
+	if (offset >= 24) {
+		// far source: all (<= 5) source words are complete in memory before this chunk
+		// starts (offset >= 20 + cnt), so they are loaded up front, one latency per chunk
 		const u8 *a = s.out + (s.out_pos - offset);
 		const u32 *A = (const u32 *)((uintptr_t)a & ~(uintptr_t)3);
 		const u32 sh = 8 * ((u32)(uintptr_t)a & 3);
-		u32 lo = A[0], hi = A[1];
-		A += 2;
-		while (length >= 4) {
-			u32 w = __funnelshift_r(lo, hi, sh);
-			lo = hi;
-			if (length > 4) hi = *A++;
-			inf_put_word(s, w);
-			length -= 4;
+		const u32 nw = (length + 3) >> 2;	// output steps
+		u32 w0 = A[0], w1 = A[1], w2 = 0, w3 = 0, w4 = 0;
+		if (nw > 1) w2 = A[2];
+		if (nw > 2) w3 = A[3];
+		if (nw > 3) w4 = A[4];
+		u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+		u32 v2 = __funnelshift_r(w2, w3, sh), v3 = __funnelshift_r(w3, w4, sh);
+		if (length >= 4) inf_put_word(s, v0);
+		if (length >= 8) inf_put_word(s, v1);
+		if (length >= 12) inf_put_word(s, v2);
+		if (length >= 16) inf_put_word(s, v3);
+		u32 r = length & 3;
+		if (r) {
+			u32 t = length < 4 ? v0 : (length < 8 ? v1 : (length < 12 ? v2 : v3));
+			inf_put_bytes(s, t & ((1u << (8 * r)) - 1), r);
 		}
-		if (length) inf_put_bytes(s, __funnelshift_r(lo, hi, sh) & ((1u << (8 * length)) - 1), length);
 	} else if (offset >= 8) {
 		// near source: a source word is only complete once the previous output word has
 		// been stored (offset >= 4 + cnt), so load right before use
@@ -300,6 +311,16 @@ __device__ __forceinline__ void inf_copy_match(inf_lane &s, u32 length, u32 offs
 			length -= 4;
 		}
 		if (length) inf_put_bytes(s, (u32)cur & ((1u << (8 * length)) - 1), length);
+	}
+}
+
+// whole match at once (unit tests)
+__device__ __forceinline__ void inf_copy_match(inf_lane &s, u32 length, u32 offset)
+{
+	while (length) {
+		u32 n = length < INF_COPY_CHUNK ? length : INF_COPY_CHUNK;
+		inf_copy_chunk(s, n, offset);
+		length -= n;
 	}
 }
 
@@ -353,9 +374,10 @@ __device__ u32 inf_parse_wrapper(const u8 *in, size_t n, int format, u32 *footer
 // to abort the stream.
 __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 {
-	// scratch inside the lane's own (about to be rebuilt) table slots: one u16 slot per value
-	u16 *lens = (u16 *)(sm + INF_SM_LTAB);	// tab_idx(i, lane), <= 320 code lengths
-	u16 *pretab = (u16 *)(sm + INF_SM_OTAB);	// tab_idx(i, lane), 128 precode entries
+	// scratch inside the lane's own (about to be rebuilt) table slots, two bytes per u16 slot:
+	// <= 320 code lengths in the litlen region, the 128-entry precode table in the offset region
+	u8 *lens = sm + INF_SM_LTAB;		// scr_idx(i, lane)
+	u8 *pretab = sm + INF_SM_OTAB;		// scr_idx(i, lane)
 	static const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 	s.is_final = inf_take(s, 1);
@@ -393,7 +415,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 				for (int q = 0; q < 19; q++)
 					if (plen[q] == 1) { sym = q; break; }
 			}
-			for (u32 i = 0; i < 128; i++) pretab[tab_idx(i, lane)] = (u16)((sym << 3) | 1);
+			for (u32 i = 0; i < 128; i++) pretab[scr_idx(i, lane)] = (u8)((sym << 3) | 1);
 		} else {
 			u32 code = 0;
 			for (u32 l = 1; l <= maxlen; l++) {
@@ -401,7 +423,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 					if (plen[sym] != l) continue;
 					u32 rev = __brev(code) >> (32 - l);
 					for (u32 i = rev; i < 128; i += 1u << l)
-						pretab[tab_idx(i, lane)] = (u16)((sym << 3) | l);
+						pretab[scr_idx(i, lane)] = (u8)((sym << 3) | l);
 					code++;
 				}
 				code <<= 1;
@@ -413,11 +435,11 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 		u32 i = 0;
 		u32 prev = 0;
 		while (i < total) {
-			u32 e = pretab[tab_idx(inf_peek(s) & 127, lane)];
+			u32 e = pretab[scr_idx(inf_peek(s) & 127, lane)];
 			s.bitpos += e & 7;
 			u32 presym = e >> 3;
 			if (presym < 16) {
-				lens[tab_idx(i, lane)] = (u16)presym;
+				lens[scr_idx(i, lane)] = (u8)presym;
 				prev = presym;
 				i++;
 				continue;
@@ -436,7 +458,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 			}
 			// running past the announced count is an error (decompress_template.h:245)
 			if (i + rep > total) return LDB_BAD_DATA;
-			for (u32 k = 0; k < rep; k++) lens[tab_idx(i + k, lane)] = (u16)val;
+			for (u32 k = 0; k < rep; k++) lens[scr_idx(i + k, lane)] = (u8)val;
 			prev = val;
 			i += rep;
 		}
@@ -719,7 +741,8 @@ __device__ __forceinline__ int inf_decode_step(inf_lane &s, const u8 *sm, const 
 		s.bitpos += eb;
 	}
 	if (offset > s.out_pos) return LDB_BAD_DATA;
-	inf_copy_match(s, length, offset);
+	s.copy_rem = length;
+	s.copy_off = offset;
 	return LDB_SUCCESS;
 }
 
@@ -736,7 +759,7 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 	s.chunk = 0xffffffffu;
 	s.in = nullptr; s.in_al = nullptr; s.in_a0 = 0; s.in_n = 0; s.in_nal = 0; s.wpos = 0; s.w0 = 0; s.w1 = 0; s.w2 = 0; s.bitpos = 0;
 	s.out = nullptr; s.out_pos = 0; s.out_avail = 0; s.acc = 0; s.cnt = 0;
-	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0;
+	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.copy_rem = 0; s.copy_off = 0;
 	bool exhausted = false;
 
 	// finishes the lane's stream with 'verdict' and makes the lane idle
@@ -789,6 +812,7 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 					s.out_avail = oa > 0xfffffff0u ? 0xfffffff0u : (u32)oa;
 					s.out_pos = 0;
 					s.acc = 0;
+					s.copy_rem = 0;
 					s.cnt = (u32)(uintptr_t)s.out & 3;	// the first word may start before 'out'
 					u32 footer;
 					u32 hdr = inf_parse_wrapper(in, n, a.format, &footer);
@@ -851,15 +875,15 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 			u32 hlit = __shfl_sync(LDB_FULL_MASK, s.hlit, owner);
 			u32 hdist = __shfl_sync(LDB_FULL_MASK, s.hdist, owner);
 			u32 is_static = __shfl_sync(LDB_FULL_MASK, s.is_static, owner);
-			const u16 *lens = (const u16 *)(sm + INF_SM_LTAB);
+			const u8 *lens = sm + INF_SM_LTAB;
 			u32 ll[9], ol[1];
 #pragma unroll
 			for (int r = 0; r < 9; r++) {
 				u32 sym = r * 32 + lane;
 				ll[r] = is_static ? inf_static_litlen_len(sym)
-						  : (sym < hlit ? lens[tab_idx(sym, owner)] : 0);
+						  : (sym < hlit ? lens[scr_idx(sym, owner)] : 0);
 			}
-			ol[0] = is_static ? 5u : (lane < hdist ? lens[tab_idx(hlit + lane, owner)] : 0);
+			ol[0] = is_static ? 5u : (lane < hdist ? lens[scr_idx(hlit + lane, owner)] : 0);
 			__syncwarp();
 			u16 *ovf_owner = (u16 *)a.overflow_scratch + ((size_t)blockIdx.x * 32 + owner) * INF_OVF_ENTRIES;
 			// offset code first, like the reference (decompress_template.h:331-332)
@@ -876,9 +900,16 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 		// ---- decode phase ----------------------------------------------------
 		for (int it = 0; it < INF_QUANTUM; it++) {
 			if (s.state == ST_DECODE) {
-				int v = inf_decode_step(s, sm, ovf, lane);
-				if (v != LDB_SUCCESS) finish(v);
-				else if (s.state == ST_HEADER && s.is_final) finish(LDB_SUCCESS);
+				if (s.copy_rem == 0) {
+					int v = inf_decode_step(s, sm, ovf, lane);
+					if (v != LDB_SUCCESS) finish(v);
+					else if (s.state == ST_HEADER && s.is_final) finish(LDB_SUCCESS);
+				}
+				if (s.copy_rem) {
+					u32 nb = s.copy_rem < INF_COPY_CHUNK ? s.copy_rem : INF_COPY_CHUNK;
+					inf_copy_chunk(s, nb, s.copy_off);
+					s.copy_rem -= nb;
+				}
 			}
 			if ((it & 31) == 31 && !__any_sync(LDB_FULL_MASK, s.state == ST_DECODE)) break;
 		}

@@ -9,11 +9,14 @@ sys.path.insert(0, ROOT)
 from libdeflate_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "lb9": [],
-    "lb8": ["-DINF_LB=8", "-DINF_LSUB_SM=128", "-DINF_OB=6", "-DINF_OSUB_SM=64"],
-    "lb8s": ["-DINF_LB=8", "-DINF_LSUB_SM=64", "-DINF_OB=6", "-DINF_OSUB_SM=64"],
-    "lb7": ["-DINF_LB=7", "-DINF_LSUB_SM=192", "-DINF_OB=6", "-DINF_OSUB_SM=64"],
-    "lb10": ["-DINF_LB=10", "-DINF_LSUB_SM=64", "-DINF_OB=7", "-DINF_OSUB_SM=64"],
+    # name: litlen main bits / smem sub entries, offset main bits / smem sub entries -> bytes per lane
+    "a_8_64_6_64": ["-DINF_LB=8", "-DINF_LSUB_SM=64", "-DINF_OB=6", "-DINF_OSUB_SM=64"],      # 896 B, 7 warps/SM (default)
+    "b_8_32_5_32": ["-DINF_LB=8", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 704 B, 9 warps
+    "c_7_64_5_32": ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 512 B, 13 warps
+    "d_7_32_5_32": ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 448 B, 15 warps
+    "e_6_96_5_32": ["-DINF_LB=6", "-DINF_LSUB_SM=96", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 448 B, 15 warps
+    "f_9_64_6_64": ["-DINF_LB=9", "-DINF_LSUB_SM=64", "-DINF_OB=6", "-DINF_OSUB_SM=64"],      # 1408 B, 4 warps
+    "g_7_96_6_64": ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"],      # 704 B, 9 warps
 }
 
 
