@@ -247,7 +247,8 @@ class DeviceBatch:
 def run_b200(args):
     import numpy as np
     import libdeflate_b200 as ldb
-    rank, world, local = dist_env()
+    from libdeflate_b200 import shard
+    rank, world, local = shard.dist_env()
     dist = None
     if world > 1:
         import torch
@@ -255,26 +256,8 @@ def run_b200(args):
         torch.cuda.set_device(local)
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
-
-    def barrier():
-        if dist:
-            dist.barrier()
-
-    def allmax(x):
-        if not dist:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if not dist:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    red = shard.Reducer(dist, "cuda" if dist else "cpu")
+    barrier, allmax, allsum = red.barrier, red.max, red.sum
 
     l = ldb.lib()
     if l.libdeflate_b200_device_count() <= local:
@@ -291,7 +274,8 @@ def run_b200(args):
     # ---- inputs: synthetic chunks generated on the host (pinned), then resident in HBM ----
     pin_in = l.libdeflate_b200_pinned_malloc(n * chunk)
     assert pin_in, "pinned_malloc failed"
-    synth.synth_fill(pin_in, chunk, rank * n, n, 0, threads)
+    first_chunk, _ = shard.shard_range(rank, world, n)
+    synth.synth_fill(pin_in, chunk, first_chunk, n, 0, threads)
     d_in = DeviceBatch(ctx, n, chunk)
     ctx._check(l.libdeflate_b200_memcpy_h2d(ctx.h, d_in.slab, pin_in, n * chunk), "h2d")
     d_in.set_sizes(np.full(n, chunk, dtype=np.uint64))

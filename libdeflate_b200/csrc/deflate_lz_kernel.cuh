@@ -72,6 +72,8 @@ struct lz_vars {
 	u32 cost_dyn, cost_static, extra_bits;
 	u32 hlit, hdist, hclen;
 	u32 n_items;
+	u32 min_len;		// shortest match worth taking (depends on the alphabet size)
+	u32 used_lits[8];	// 256-bit set of byte values seen in the first 4 KiB
 	u32 carry;		// partial output word at bit position obit (persists between flushes)
 	u32 nused_lit, nused_off;
 	u32 failed;
@@ -102,6 +104,27 @@ __device__ __forceinline__ lz_params lz_level_params(int level)
 	case 11: return {500, 258, 1};
 	default: return {800, 258, 1};
 	}
+}
+
+// Shortest match length worth emitting, from the number of distinct byte values at the start
+// of the input (few distinct literals => literals are cheap => short matches do not pay) and
+// the search depth (shallow searches find worse matches, so be less picky).  Same heuristic as
+// the reference's choose_min_match_len (lib/deflate_compress.c:2296-2326), restated as
+// thresholds; our match finder starts at length 4.
+__device__ __forceinline__ u32 lz_choose_min_len(u32 num_used_literals, u32 depth)
+{
+	u32 m;
+	if (num_used_literals < 6) m = 9;
+	else if (num_used_literals < 8) m = 8;
+	else if (num_used_literals < 10) m = 7;
+	else if (num_used_literals < 16) m = 6;
+	else if (num_used_literals < 45) m = 5;
+	else m = 4;
+	if (depth < 16) {
+		u32 cap = depth < 5 ? 4 : (depth < 10 ? 5 : 7);
+		if (m > cap) m = cap;
+	}
+	return m;
 }
 
 // ---- ring access ------------------------------------------------------------------
@@ -451,6 +474,21 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				loaded_end = to;
 			}
 			if (b0 == 0) {
+				// alphabet size of the first 4 KiB -> minimum match length (ref:
+				// calculate_min_match_len, lib/deflate_compress.c:2329-2346)
+				if (tid < 8) v->used_lits[tid] = 0;
+				__syncthreads();
+				const u32 scan = n < 4096 ? n : 4096;
+				for (u32 i = tid; i < scan; i += LZ_THREADS) {
+					u32 b = ring[i];
+					atomicOr(&v->used_lits[b >> 5], 1u << (b & 31));
+				}
+				__syncthreads();
+				if (tid == 0) {
+					u32 cnt = 0;
+					for (int k = 0; k < 8; k++) cnt += __popc(v->used_lits[k]);
+					v->min_len = n < 512 ? 4 : lz_choose_min_len(cnt, (u32)P.depth);
+				}
 				if (warp == 0) lz_insert_batch(ring, head, nextt, 0, n, lane);
 				__syncthreads();
 			}
@@ -493,8 +531,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 								const u32 cp = p - dist;
 								prev_dist = dist;
 								cand = nextt[cp & (LZ_WIN - 1)];
-								// a longer match must agree on the last 4 bytes of the current best
-								// (ref: hc_matchfinder.h:301-304) and on the first 4
+								// a longer match must agree on the byte just past the current best (cheap
+								// one-byte test first), on its last 4 bytes (ref: hc_matchfinder.h:301-304)
+								// and on the first 4
+								if (lz_ld8(ring, cp + tailo + 3) != (tailv >> 24)) continue;
 								if (lz_ld32(ring, cp + tailo) != tailv) continue;
 								if (tailo && lz_ld32(ring, cp) != cur) continue;
 								u32 len = 4;
@@ -528,8 +568,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			for (u32 w = warp; w < LZ_NWIN; w += LZ_WARPS) {
 				u32 i = w * 32 + lane;
 				u32 p = b0 + i;
+				const u32 min_len = v->min_len;
 				u32 L0 = rlen[i], O0 = (roff[i] & 0x7fff) + 1;
-				bool is_match = L0 >= 4 && p < n;
+				bool is_match = L0 >= min_len && p < n;
 				if (is_match && P.lazy && i + 1 < LZ_BATCH) {
 					u32 L1 = rlen[i + 1], O1 = (roff[i + 1] & 0x7fff) + 1;
 					// ref: deflate_compress.c:2722-2725 -- prefer the next position's match if clearly better

@@ -72,7 +72,13 @@
 #define INF_OVF_ENTRIES (INF_OVF_L + INF_OVF_O)
 
 #ifndef INF_QUANTUM
-#define INF_QUANTUM   192		// decode iterations between service phases
+#define INF_QUANTUM   96		// decode iterations between service phases
+#endif
+#ifndef INF_LIT_ROUNDS
+#define INF_LIT_ROUNDS 4		// litlen rounds per match round
+#endif
+#ifndef INF_LIT_MIN_LANES
+#define INF_LIT_MIN_LANES 10	// stop the litlen rounds when fewer lanes than this still decode literals
 #endif
 
 // per-warp shared memory layout (bytes)
@@ -121,6 +127,7 @@ struct inf_lane {
 	u32 hlit, hdist, is_static;
 	u32 stored_len, stored_src;
 	u32 copy_rem, copy_off;	// match bytes still to be copied (continued across iterations)
+	u32 pend_len;		// decoded match length whose offset has not been decoded yet
 	// bookkeeping
 	u32 chunk;		// chunk index
 	u32 hdr_bytes;		// wrapper header size
@@ -252,7 +259,9 @@ __device__ __forceinline__ void inf_reload_pending(inf_lane &s)
 
 // Copies 'length' (<= INF_COPY_CHUNK) bytes of a match.  Long matches are continued by the
 // caller in later iterations so that one long match does not stall the other 31 lanes.
+#ifndef INF_COPY_CHUNK
 #define INF_COPY_CHUNK 16
+#endif
 __device__ __forceinline__ void inf_copy_chunk(inf_lane &s, u32 length, u32 offset)
 {
 	if (offset >= 24) {
@@ -671,12 +680,14 @@ __device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
 	return sym < 144 ? 8 : (sym < 256 ? 9 : (sym < 280 ? 7 : 8));
 }
 
-// ---- one decode step (one litlen symbol, plus the match if it is a length) ----------
-__device__ __forceinline__ int inf_decode_step(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
+// ---- decoding, split in two so that the warp can run several cheap litlen rounds (most
+// symbols are literals) before it pays for ONE expensive match round with many lanes in it --
+//
+// inf_decode_litlen: one litlen symbol.  Literal -> stored.  End of block -> state ST_HEADER.
+// Length -> s.pend_len set (> 0); the offset is decoded by inf_decode_offset.
+__device__ __forceinline__ int inf_decode_litlen(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
 {
 	const u16 *ltab = (const u16 *)(sm + INF_SM_LTAB);
-	const u16 *otab = (const u16 *)(sm + INF_SM_OTAB);
-
 	u32 bits = inf_peek(s);
 	if (s.wpos + 8 > s.in_nal) {
 		// virtual zero bytes are (nearly) in play: P >= 8n+9 means the reference's refill
@@ -717,8 +728,15 @@ __device__ __forceinline__ int inf_decode_step(inf_lane &s, const u8 *sm, const 
 		length = 258;
 	}
 	if (length > s.out_avail - s.out_pos) return LDB_INSUFFICIENT_SPACE;
+	s.pend_len = length;
+	return LDB_SUCCESS;
+}
 
-	bits = inf_peek(s);
+// inf_decode_offset: the offset of the pending length; arms the copy.
+__device__ __forceinline__ int inf_decode_offset(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
+{
+	const u16 *otab = (const u16 *)(sm + INF_SM_OTAB);
+	u32 bits = inf_peek(s);
 	u32 oe = otab[tab_idx(bits & (INF_OMAIN - 1), lane)];
 	if (oe & OE_SUB_FLAG) {
 		u32 sstart = (oe >> 4) & 0x3ff;
@@ -741,8 +759,9 @@ __device__ __forceinline__ int inf_decode_step(inf_lane &s, const u8 *sm, const 
 		s.bitpos += eb;
 	}
 	if (offset > s.out_pos) return LDB_BAD_DATA;
-	s.copy_rem = length;
+	s.copy_rem = s.pend_len;
 	s.copy_off = offset;
+	s.pend_len = 0;
 	return LDB_SUCCESS;
 }
 
@@ -759,7 +778,7 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 	s.chunk = 0xffffffffu;
 	s.in = nullptr; s.in_al = nullptr; s.in_a0 = 0; s.in_n = 0; s.in_nal = 0; s.wpos = 0; s.w0 = 0; s.w1 = 0; s.w2 = 0; s.bitpos = 0;
 	s.out = nullptr; s.out_pos = 0; s.out_avail = 0; s.acc = 0; s.cnt = 0;
-	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.copy_rem = 0; s.copy_off = 0;
+	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.copy_rem = 0; s.copy_off = 0; s.pend_len = 0;
 	bool exhausted = false;
 
 	// finishes the lane's stream with 'verdict' and makes the lane idle
@@ -813,6 +832,7 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 					s.out_pos = 0;
 					s.acc = 0;
 					s.copy_rem = 0;
+					s.pend_len = 0;
 					s.cnt = (u32)(uintptr_t)s.out & 3;	// the first word may start before 'out'
 					u32 footer;
 					u32 hdr = inf_parse_wrapper(in, n, a.format, &footer);
@@ -899,19 +919,31 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 
 		// ---- decode phase ----------------------------------------------------
 		for (int it = 0; it < INF_QUANTUM; it++) {
-			if (s.state == ST_DECODE) {
-				if (s.copy_rem == 0) {
-					int v = inf_decode_step(s, sm, ovf, lane);
+			// litlen rounds: lanes keep decoding literals until they hit a length (or the end
+			// of their block); stops early once most lanes wait for the match round
+#pragma unroll 1
+			for (int r = 0; r < INF_LIT_ROUNDS; r++) {
+				if (s.state == ST_DECODE && s.pend_len == 0 && s.copy_rem == 0) {
+					int v = inf_decode_litlen(s, sm, ovf, lane);
 					if (v != LDB_SUCCESS) finish(v);
 					else if (s.state == ST_HEADER && s.is_final) finish(LDB_SUCCESS);
 				}
-				if (s.copy_rem) {
-					u32 nb = s.copy_rem < INF_COPY_CHUNK ? s.copy_rem : INF_COPY_CHUNK;
-					inf_copy_chunk(s, nb, s.copy_off);
-					s.copy_rem -= nb;
-				}
+				if (r + 1 < INF_LIT_ROUNDS &&
+				    __popc(__ballot_sync(LDB_FULL_MASK, s.state == ST_DECODE && s.pend_len == 0 && s.copy_rem == 0)) < INF_LIT_MIN_LANES)
+					break;
 			}
-			if ((it & 31) == 31 && !__any_sync(LDB_FULL_MASK, s.state == ST_DECODE)) break;
+			// match round: offsets of the pending lengths, then one bounded piece of every
+			// pending copy
+			if (s.state == ST_DECODE && s.pend_len) {
+				int v = inf_decode_offset(s, sm, ovf, lane);
+				if (v != LDB_SUCCESS) finish(v);
+			}
+			if (s.state == ST_DECODE && s.copy_rem) {
+				u32 nb = s.copy_rem < INF_COPY_CHUNK ? s.copy_rem : INF_COPY_CHUNK;
+				inf_copy_chunk(s, nb, s.copy_off);
+				s.copy_rem -= nb;
+			}
+			if ((it & 15) == 15 && !__any_sync(LDB_FULL_MASK, s.state == ST_DECODE)) break;
 		}
 		__syncwarp();
 	}

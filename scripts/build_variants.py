@@ -8,15 +8,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from libdeflate_b200 import build as b  # noqa: E402
 
+GEO_A = ["-DINF_LB=8", "-DINF_LSUB_SM=64", "-DINF_OB=6", "-DINF_OSUB_SM=64"]      # 896 B/lane, 7 warps/SM (default)
+GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]      # 704 B, 9 warps
+GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
+GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    # name: litlen main bits / smem sub entries, offset main bits / smem sub entries -> bytes per lane
-    "a_8_64_6_64": ["-DINF_LB=8", "-DINF_LSUB_SM=64", "-DINF_OB=6", "-DINF_OSUB_SM=64"],      # 896 B, 7 warps/SM (default)
-    "b_8_32_5_32": ["-DINF_LB=8", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 704 B, 9 warps
-    "c_7_64_5_32": ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 512 B, 13 warps
-    "d_7_32_5_32": ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 448 B, 15 warps
-    "e_6_96_5_32": ["-DINF_LB=6", "-DINF_LSUB_SM=96", "-DINF_OB=5", "-DINF_OSUB_SM=32"],      # 448 B, 15 warps
-    "f_9_64_6_64": ["-DINF_LB=9", "-DINF_LSUB_SM=64", "-DINF_OB=6", "-DINF_OSUB_SM=64"],      # 1408 B, 4 warps
-    "g_7_96_6_64": ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"],      # 704 B, 9 warps
+    "a_r1": GEO_A + ["-DINF_LIT_ROUNDS=1"],
+    "a_r2": GEO_A + ["-DINF_LIT_ROUNDS=2"],
+    "a_r6": GEO_A + ["-DINF_LIT_ROUNDS=6"],
+    "a_c8": GEO_A + ["-DINF_COPY_CHUNK=8"],
+    "g_r4": GEO_G,
+    "c_r4": GEO_C,
+    "d_r4": GEO_D,
+    "c_r6": GEO_C + ["-DINF_LIT_ROUNDS=6", "-DINF_LIT_MIN_LANES=8"],
 }
 
 
