@@ -16,10 +16,12 @@
 //   * each lane's decode tables live in shared memory, lane-interleaved
 //     (entry i of lane t sits in bank t), so the 32 data-dependent lookups of a
 //     warp instruction are bank-conflict free by construction;
-//   * tables are compact 16-bit entries: 9-bit main litlen table + 128 subtable
-//     entries, 6-bit main offset table + 64 subtable entries = 1536 B per lane,
-//     48 KiB per warp, 4 warps per SM; the (rare) excess subtable entries of an
-//     adversarial code spill to a per-lane global scratch;
+//   * tables are compact 16-bit entries: 7-bit main litlen table + 32 subtable
+//     entries, 5-bit main offset table + 32 subtable entries = 448 B per lane,
+//     14 KiB per warp, 14 single-warp CTAs per SM (occupancy is what this
+//     latency-bound kernel lives on: 4 -> 7 -> 14 warps/SM measured 31 -> 65 ->
+//     141 GB/s); subtable entries beyond the shared-memory capacity live in a
+//     per-lane global scratch (L1/L2 resident);
 //   * block headers are parsed by the owning lane, then the WARP builds that
 //     lane's tables cooperatively (ballot/match_any ranking, strided fills);
 //   * stored blocks are copied by the whole warp, coalesced;
@@ -48,19 +50,19 @@
 
 // table geometry (overridable at build time for tuning sweeps, see scripts/build_variants.py)
 #ifndef INF_LB
-#define INF_LB        8			// main litlen table bits
+#define INF_LB        7			// main litlen table bits
 #endif
 #define INF_LMAIN     (1 << INF_LB)
 #ifndef INF_LSUB_SM
-#define INF_LSUB_SM   64		// litlen subtable entries kept in shared memory
+#define INF_LSUB_SM   32		// litlen subtable entries kept in shared memory
 #endif
 #define INF_LSUB_CAP  1024		// total litlen subtable capacity (rest in global scratch)
 #ifndef INF_OB
-#define INF_OB        6			// main offset table bits
+#define INF_OB        5			// main offset table bits
 #endif
 #define INF_OMAIN     (1 << INF_OB)
 #ifndef INF_OSUB_SM
-#define INF_OSUB_SM   64
+#define INF_OSUB_SM   32
 #endif
 #define INF_OSUB_CAP  1024
 #define INF_L_ENTRIES (INF_LMAIN + INF_LSUB_SM)		// 640 u16 per lane
