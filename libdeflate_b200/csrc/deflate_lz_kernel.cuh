@@ -36,33 +36,41 @@
 
 #define LZ_THREADS   512
 #define LZ_WARPS     (LZ_THREADS / 32)
-#define LZ_BATCH     4096			// positions searched/parsed per round
-#define LZ_NWIN      (LZ_BATCH / 32)
-#define LZ_SEG       16384			// TMA load granularity
+#define LZ_PASS      32768			// positions matched + parsed per pass = one DEFLATE block
+#define LZ_NWIN      (LZ_PASS / 32)
+#define LZ_RUN       (LZ_PASS / LZ_THREADS)	// consecutive positions owned by one searcher thread
+#define LZ_SEG       16384			// largest single TMA load
 #define LZ_RING      65536
-#define LZ_HASH_BITS 15
+#define LZ_HASH_BITS 13
 #define LZ_WIN       32768
-#define LZ_BLOCK_IN  32768			// target input bytes per DEFLATE block
-#define LZ_MIN_BLOCK 5000			// ref: MIN_BLOCK_LENGTH (deflate_compress.c:66) -- keeps compress_bound valid
-#define LZ_TOKCAP    (LZ_BLOCK_IN + LZ_MIN_BLOCK + LZ_BATCH + 512)
+#define LZ_LOOKAHEAD 512			// bytes past the pass kept in the ring (>= 258 + 8)
+#define LZ_MAX_DIST  (LZ_WIN - LZ_LOOKAHEAD)	// the oldest LOOKAHEAD bytes of the window are overwritten
+#define LZ_TOKCAP    (LZ_PASS + 64)
 #define LZ_STAGE_WORDS 2048			// 8 KiB emission staging
 #define LZ_EMIT_ROUND  1024			// tokens per emission round (<= 48 bits each)
 
 // shared memory layout
 #define LZ_SM_RING   0
-#define LZ_SM_HEAD   (LZ_SM_RING + LZ_RING)
-#define LZ_SM_NEXT   (LZ_SM_HEAD + 2 * (1 << LZ_HASH_BITS))
-#define LZ_SM_RLEN   (LZ_SM_NEXT + 2 * LZ_WIN)		// u16[BATCH]  (also: hashes; Huffman scratch; staging)
-#define LZ_SM_ROFF   (LZ_SM_RLEN + 2 * LZ_BATCH)	// u16[BATCH]
-#define LZ_SM_EXIT   (LZ_SM_ROFF + 2 * LZ_BATCH)	// u16[BATCH]
-#define LZ_SM_VIS    (LZ_SM_EXIT + 2 * LZ_BATCH)	// u32[NWIN]
-#define LZ_SM_TOKOFF (LZ_SM_VIS + 4 * LZ_NWIN)		// u32[NWIN + 1]
-#define LZ_SM_ENTRY  (LZ_SM_TOKOFF + 4 * (LZ_NWIN + 4))	// u8[NWIN]
-#define LZ_SM_FREQ   (LZ_SM_ENTRY + LZ_NWIN)		// u32[288 + 32]
-#define LZ_SM_LENS   (LZ_SM_FREQ + 4 * 320)		// u8[320]
-#define LZ_SM_CODES  (LZ_SM_LENS + 320)			// u16[320]
-#define LZ_SM_VARS   (LZ_SM_CODES + 2 * 320)		// misc scalars, mbarrier
+#define LZ_SM_NEXT   (LZ_SM_RING + LZ_RING)			// u16[65536], indexed by pos mod 65536
+#define LZ_SM_HEAD   (LZ_SM_NEXT + 2 * 65536)			// u16[1 << HASH_BITS]
+#define LZ_SM_R      (LZ_SM_HEAD + 2 * (1 << LZ_HASH_BITS))	// 12 KiB multi-purpose region:
+#define LZ_SM_VIS    (LZ_SM_R)					//   parse: u32[NWIN] visited masks
+#define LZ_SM_TOKOFF (LZ_SM_R + 4096)				//   parse: u32[NWIN + 16] token offsets
+#define LZ_SM_ENTRY  (LZ_SM_R + 8320)				//   parse: u8[NWIN] entry lane per window
+#define LZ_SM_ESCAN  (LZ_SM_R + 9344)				//   emission: scan scratch u32[80]
+#define LZ_SM_ITEMS  (LZ_SM_R + 12288)				// u16[512] precode items
+#define LZ_SM_FREQ   (LZ_SM_ITEMS + 1024)			// u32[288 + 32]
+#define LZ_SM_LENS   (LZ_SM_FREQ + 4 * 320)			// u8[320]
+#define LZ_SM_CODES  (LZ_SM_LENS + 320)				// u16[320]
+#define LZ_SM_VARS   (LZ_SM_CODES + 2 * 320)			// misc scalars, mbarrier
 #define LZ_SM_BYTES  (LZ_SM_VARS + 256)
+
+// per-CTA global scratch (L2 resident): per-position results of the current pass + tokens
+#define LZ_GS_RLEN   0						// u16[PASS]
+#define LZ_GS_ROFF   (LZ_GS_RLEN + 2 * LZ_PASS)			// u16[PASS]
+#define LZ_GS_EXIT   (LZ_GS_ROFF + 2 * LZ_PASS)			// u16[PASS]
+#define LZ_GS_TOK    (LZ_GS_EXIT + 2 * LZ_PASS)			// u32[TOKCAP]
+#define LZ_GS_BYTES  (LZ_GS_TOK + 4 * LZ_TOKCAP)
 
 struct lz_vars {
 	unsigned long long mbar;
@@ -325,17 +333,18 @@ __device__ __forceinline__ void lz_gen_codes_serial(const u8 *lens, u32 nsyms, u
 	}
 }
 
-// ---- ordered hash-chain insertion of one batch, executed by ONE warp ------------------------
-// For every position p of the batch: next[p] = most recent earlier position with the same
-// 4-byte hash, head[hash] = p (ref semantics: hc_matchfinder.h:227-232).  Same-hash lanes of a
-// 32-position tile are resolved with __match_any_sync; the tile's reads of head[] happen before
-// its writes (two phases).
-__device__ __forceinline__ void lz_insert_batch(const u8 *ring, u16 *head, u16 *nextt, u32 b0, u32 n, u32 lane)
+// ---- ordered hash-chain insertion of one pass, executed by ONE warp --------------------------
+// For every position p: next[p] = most recent earlier position with the same 4-byte hash,
+// head[hash] = p (ref semantics: hc_matchfinder.h:227-232).  Same-hash lanes of a 32-position
+// tile are resolved with __match_any_sync; the tile's reads of head[] happen before its writes.
+// next[] has one slot per position mod 65536, so inserting a pass only reuses slots of
+// positions 64 KiB back -- outside every window -- and searches never see a clobbered link.
+__device__ __forceinline__ void lz_insert_pass(const u8 *ring, u16 *head, u16 *nextt, u32 b0, u32 pend, u32 n, u32 lane)
 {
 	const u32 lt = (1u << lane) - 1;
-	for (u32 t = 0; t < LZ_NWIN; t++) {
-		const u32 p = b0 + t * 32 + lane;
-		const bool valid = p + 4 <= n;
+	for (u32 base = b0; base < pend; base += 32) {
+		const u32 p = base + lane;
+		const bool valid = p < pend && p + 4 <= n;
 		const u32 h = valid ? lz_hash(lz_ld32(ring, p)) : 0;
 		const u32 m = __match_any_sync(LDB_FULL_MASK, valid ? h : (0x10000u | lane));
 		const u32 old_head = valid ? head[h] : 0;
@@ -343,11 +352,58 @@ __device__ __forceinline__ void lz_insert_batch(const u8 *ring, u16 *head, u16 *
 		if (valid) {
 			const u32 below = m & lt;
 			const u32 pred = below ? (p - lane + (31 - __clz(below))) & 0xffff : old_head;
-			nextt[p & (LZ_WIN - 1)] = (u16)pred;
+			nextt[p & 0xffff] = (u16)pred;
 			if ((m >> lane) == 1) head[h] = (u16)p;	// highest lane of the group
 		}
 		__syncwarp();
-		if (b0 + t * 32 + 32 >= n) break;
+	}
+}
+
+// ---- one chain search (ref: hc_matchfinder.h:182-338) ------------------------------------------
+// Walks the hash chain of position p (newest first, at most 'depth' candidates within
+// LZ_MAX_DIST) and returns the longest match; (best_len, best_dist) may come in pre-seeded with
+// a match carried over from position p-1.  Candidates are filtered by one byte just past the
+// current best, then its last 4 bytes (hc_matchfinder.h:301-304), then the first 4.
+__device__ __forceinline__ void lz_search(const u8 *ring, const u16 *nextt, u32 p, u32 n, int depth, u32 nice_level,
+					   u32 &best_len, u32 &best_dist)
+{
+	const u32 max_len = n - p < 258 ? n - p : 258;
+	const u32 nice = nice_level < max_len ? nice_level : max_len;
+	if (best_len) {
+		// a carried-over match may continue past where its predecessor was capped
+		while (best_len < max_len && lz_ld8(ring, p + best_len) == lz_ld8(ring, p - best_dist + best_len)) best_len++;
+	}
+	if (best_len >= nice) return;
+	const u32 cur = lz_ld32(ring, p);
+	u32 tailo = best_len >= 4 ? best_len - 3 : 0;
+	u32 tailv = tailo ? lz_ld32(ring, p + tailo) : cur;
+	const u32 lim = p < LZ_MAX_DIST ? p : LZ_MAX_DIST;
+	u32 cand = nextt[p & 0xffff];
+	u32 prev_dist = 0;
+	for (int d = 0; d < depth; d++) {
+		const u32 dist = (p - cand) & 0xffff;
+		if (dist - 1 >= lim || dist <= prev_dist) break;
+		prev_dist = dist;
+		const u32 cq = cand;			// ring index of the candidate (positions are stored mod 65536)
+		cand = nextt[cq];
+		if (lz_ld8(ring, cq + tailo + 3) != (tailv >> 24)) continue;
+		if (lz_ld32(ring, cq + tailo) != tailv) continue;
+		if (tailo && lz_ld32(ring, cq) != cur) continue;
+		u32 len = 4;
+		while (len + 4 <= max_len) {
+			u32 x = lz_ld32(ring, p + len) ^ lz_ld32(ring, cq + len);
+			if (x) { len += (__ffs(x) - 1) >> 3; goto extended; }
+			len += 4;
+		}
+		while (len < max_len && lz_ld8(ring, p + len) == lz_ld8(ring, cq + len)) len++;
+	extended:
+		if (len > best_len) {
+			best_len = len;
+			best_dist = dist;
+			if (len >= nice) break;
+			tailo = len - 3;
+			tailv = lz_ld32(ring, p + tailo);
+		}
 	}
 }
 
@@ -359,29 +415,32 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 	u8 *ring = sm + LZ_SM_RING;
 	u16 *head = (u16 *)(sm + LZ_SM_HEAD);
 	u16 *nextt = (u16 *)(sm + LZ_SM_NEXT);
-	u16 *rlen = (u16 *)(sm + LZ_SM_RLEN);
-	u16 *roff = (u16 *)(sm + LZ_SM_ROFF);
-	u16 *exitt = (u16 *)(sm + LZ_SM_EXIT);
 	u32 *vis = (u32 *)(sm + LZ_SM_VIS);
 	u32 *tokoff = (u32 *)(sm + LZ_SM_TOKOFF);
 	u8 *entryt = sm + LZ_SM_ENTRY;
+	u32 *escan = (u32 *)(sm + LZ_SM_ESCAN);
 	u32 *freq = (u32 *)(sm + LZ_SM_FREQ);
 	u8 *lens = sm + LZ_SM_LENS;
 	u16 *codes = (u16 *)(sm + LZ_SM_CODES);
 	lz_vars *v = (lz_vars *)(sm + LZ_SM_VARS);
-	// block-flush scratch aliases the batch arrays (never live at the same time)
-	u32 *stage = (u32 *)(sm + LZ_SM_RLEN);				// 8 KiB
-	u16 *hsorted = (u16 *)(sm + LZ_SM_ROFF);			// 288 * 2
-	u32 *hnodefreq = (u32 *)(sm + LZ_SM_ROFF + 1024);		// 576 * 4
-	u16 *hparent = (u16 *)(sm + LZ_SM_ROFF + 1024 + 2304);		// 576 * 2
-	u16 *items = (u16 *)(sm + LZ_SM_EXIT);				// precode items (<= 320 + slack)
-	u16 *osorted = (u16 *)(sm + LZ_SM_EXIT + 1024);
-	u32 *onodefreq = (u32 *)(sm + LZ_SM_EXIT + 1024 + 128);
-	u16 *oparent = (u16 *)(sm + LZ_SM_EXIT + 1024 + 128 + 512);
+	// block-flush scratch aliases the parse region R (never live at the same time)
+	u32 *stage = (u32 *)(sm + LZ_SM_R);				// 8 KiB
+	u16 *hsorted = (u16 *)(sm + LZ_SM_R);				// 288 * 2
+	u32 *hnodefreq = (u32 *)(sm + LZ_SM_R + 1024);			// 576 * 4
+	u16 *hparent = (u16 *)(sm + LZ_SM_R + 1024 + 2304);		// 576 * 2
+	u16 *osorted = (u16 *)(sm + LZ_SM_R + 4608);
+	u32 *onodefreq = (u32 *)(sm + LZ_SM_R + 4608 + 128);
+	u16 *oparent = (u16 *)(sm + LZ_SM_R + 4608 + 128 + 512);
+	u16 *items = (u16 *)(sm + LZ_SM_ITEMS);				// precode items (<= 320 + slack)
+	// per-position results of the current pass live in this CTA's global scratch
+	u8 *gs = a.scratch + (size_t)blockIdx.x * LZ_GS_BYTES;
+	u16 *rlen = (u16 *)(gs + LZ_GS_RLEN);
+	u16 *roff = (u16 *)(gs + LZ_GS_ROFF);
+	u16 *exitt = (u16 *)(gs + LZ_GS_EXIT);
+	u32 *tokbuf = (u32 *)(gs + LZ_GS_TOK);
 
 	const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const lz_params P = lz_level_params(a.level);
-	u32 *tokbuf = (u32 *)(a.scratch) + (size_t)blockIdx.x * LZ_TOKCAP;
 
 	if (tid == 0) {
 		v->tma_phase = 0;
@@ -461,17 +520,22 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		__syncthreads();
 
 		u32 loaded_end = 0;
-		u32 block_begin = 0;		// input position where the current block's tokens start
-		u32 next_block_cut = n - 0 < LZ_BLOCK_IN + LZ_MIN_BLOCK ? n : LZ_BLOCK_IN;
 
-		for (u32 b0 = 0; b0 < n; b0 += LZ_BATCH) {
-			const u32 bend = b0 + LZ_BATCH < n ? b0 + LZ_BATCH : n;
-			// (a) window staging: searching batch b needs [b0 - 32768, bend + 258 + 4); inserting
-			// batch b+1 (which overlaps the search, see below) needs up to b0 + 2*BATCH + 3
-			while (loaded_end < n && loaded_end < b0 + 2 * LZ_BATCH + 512) {
-				u32 to = loaded_end + LZ_SEG < n ? loaded_end + LZ_SEG : n;
-				lz_load_segment(sm, v, in, loaded_end, to);
-				loaded_end = to;
+		for (u32 b0 = 0; b0 < n; b0 += LZ_PASS) {
+			const u32 pend = b0 + LZ_PASS < n ? b0 + LZ_PASS : n;
+			const u32 block_begin = b0, block_end = pend;
+			const bool last = pend >= n;
+			// (a) window staging by the TMA engine: the ring holds [b0 - MAX_DIST, pend + LOOKAHEAD)
+			{
+				const u32 want = pend + LZ_LOOKAHEAD < n ? pend + LZ_LOOKAHEAD : n;
+				while (loaded_end < want) {
+					// a segment must not wrap around the ring
+					u32 room = LZ_RING - (loaded_end & (LZ_RING - 1));
+					u32 to = loaded_end + (room < LZ_SEG ? room : LZ_SEG);
+					if (to > want) to = want;
+					lz_load_segment(sm, v, in, loaded_end, to);
+					loaded_end = to;
+				}
 			}
 			if (b0 == 0) {
 				// alphabet size of the first 4 KiB -> minimum match length (ref:
@@ -480,8 +544,8 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				__syncthreads();
 				const u32 scan = n < 4096 ? n : 4096;
 				for (u32 i = tid; i < scan; i += LZ_THREADS) {
-					u32 b = ring[i];
-					atomicOr(&v->used_lits[b >> 5], 1u << (b & 31));
+					u32 bv = ring[i];
+					atomicOr(&v->used_lits[bv >> 5], 1u << (bv & 31));
 				}
 				__syncthreads();
 				if (tid == 0) {
@@ -489,89 +553,83 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					for (int k = 0; k < 8; k++) cnt += __popc(v->used_lits[k]);
 					v->min_len = n < 512 ? 4 : lz_choose_min_len(cnt, (u32)P.depth);
 				}
-				if (warp == 0) lz_insert_batch(ring, head, nextt, 0, n, lane);
 				__syncthreads();
 			}
-			// (b) warp 0 inserts the NEXT batch into the hash chains (ordered, ref semantics:
-			// hc_matchfinder.h:227-232) while the other 15 warps search THIS batch.  Searches
-			// only follow next[] links that point backwards, so later insertions cannot mislead
-			// them (a clobbered link at the far edge of the window fails the monotonic check).
-			if (warp == 0) {
-				if (b0 + LZ_BATCH < n) lz_insert_batch(ring, head, nextt, b0 + LZ_BATCH, n, lane);
-			} else {
-				// each searcher owns a run of consecutive positions and carries the match of
-				// position p over to p+1 (same distance, one byte shorter): long matches are
-				// extended once, and the prefilter rejects most chain candidates cheaply
-				const u32 st = tid - 32;
-				const u32 i_begin = (st * LZ_BATCH) / (LZ_THREADS - 32);
-				const u32 i_end = ((st + 1) * LZ_BATCH) / (LZ_THREADS - 32);
-				u32 inh_len = 0, inh_dist = 0;
-				for (u32 i = i_begin; i < i_end; i++) {
+			// (b) ordered chain insertion of the whole pass (one warp)
+			if (warp == 0) lz_insert_pass(ring, head, nextt, b0, pend, n, lane);
+			__syncthreads();
+			// (c) guided search.  Every thread owns a run of LZ_RUN consecutive positions and
+			// walks it like the reference's lazy parser (deflate_compress.c:2605-2808): search
+			// where a token could start, look one position ahead, then skip the positions the
+			// chosen match covers (they inherit the match, one byte shorter each).  Every
+			// position still gets a (length, distance) so that the exact, parallel parse below
+			// can start a token anywhere.
+			{
+				const u32 min_len = v->min_len;
+				const u32 i_begin = tid * LZ_RUN;
+				const u32 i_end = i_begin + LZ_RUN;
+				u32 i = i_begin;
+				u32 L = 0, D = 0;
+				bool have = false;
+				while (i < i_end) {
 					const u32 p = b0 + i;
-					u32 best_len = inh_len, best_dist = inh_dist;
-					if (p + 4 <= n) {
-						const u32 max_len = n - p < 258 ? n - p : 258;
-						const u32 nice = (u32)P.nice < max_len ? (u32)P.nice : max_len;
-						// the carried-over match may continue past where its predecessor was capped
-						if (best_len)
-							while (best_len < max_len && lz_ld8(ring, p + best_len) == lz_ld8(ring, p - best_dist + best_len)) best_len++;
-						if (best_len < nice) {
-							const u32 cur = lz_ld32(ring, p);
-							u32 tailv = best_len >= 4 ? lz_ld32(ring, p + best_len - 3) : cur;
-							u32 tailo = best_len >= 4 ? best_len - 3 : 0;
-							// candidates older than this have had their next[] slot reused by the batch
-							// being inserted concurrently: end of chain (keeps the output deterministic)
-							const u32 wnd = LZ_WIN - 2 * LZ_BATCH + i;
-							const u32 lim = p < wnd ? p : wnd;
-							u32 cand = nextt[p & (LZ_WIN - 1)];
-							u32 prev_dist = 0;
-							for (int d = 0; d < P.depth; d++) {
-								const u32 dist = (p - cand) & 0xffff;
-								if (dist - 1 >= lim || dist <= prev_dist) break;
-								const u32 cp = p - dist;
-								prev_dist = dist;
-								cand = nextt[cp & (LZ_WIN - 1)];
-								// a longer match must agree on the byte just past the current best (cheap
-								// one-byte test first), on its last 4 bytes (ref: hc_matchfinder.h:301-304)
-								// and on the first 4
-								if (lz_ld8(ring, cp + tailo + 3) != (tailv >> 24)) continue;
-								if (lz_ld32(ring, cp + tailo) != tailv) continue;
-								if (tailo && lz_ld32(ring, cp) != cur) continue;
-								u32 len = 4;
-								while (len + 4 <= max_len) {
-									u32 x = lz_ld32(ring, p + len) ^ lz_ld32(ring, cp + len);
-									if (x) { len += (__ffs(x) - 1) >> 3; goto extended; }
-									len += 4;
-								}
-								while (len < max_len && lz_ld8(ring, p + len) == lz_ld8(ring, cp + len)) len++;
-							extended:
-								if (len > best_len) {
-									best_len = len;
-									best_dist = dist;
-									if (len >= nice) break;
-									tailo = len - 3;
-									tailv = lz_ld32(ring, p + tailo);
-								}
-							}
-						}
-					} else {
-						best_len = 0;
+					if (p >= pend) break;
+					if (p + 4 > n) {
+						rlen[i] = 0;
+						roff[i] = 0;
+						i++;
+						have = false;
+						continue;
 					}
-					rlen[i] = (u16)best_len;
-					roff[i] = (u16)(best_len ? best_dist - 1 : 0);
-					inh_len = best_len >= 5 ? best_len - 1 : 0;
-					inh_dist = best_dist;
+					if (!have) {
+						L = 0; D = 0;
+						lz_search(ring, nextt, p, n, P.depth, (u32)P.nice, L, D);
+						rlen[i] = (u16)L;
+						roff[i] = (u16)(L ? D - 1 : 0);
+					}
+					have = false;
+					if (L < min_len) { i++; continue; }
+					u32 covered_from = i + 1;	// first position whose result is still to be written
+					if (P.lazy && L < (u32)P.nice && i + 1 < i_end && p + 1 + 4 <= n && p + 1 < pend) {
+						u32 L1 = L - 1 >= 4 ? L - 1 : 0, D1 = D;
+						lz_search(ring, nextt, p + 1, n, P.depth >> 1, (u32)P.nice, L1, D1);
+						rlen[i + 1] = (u16)L1;
+						roff[i + 1] = (u16)(L1 ? D1 - 1 : 0);
+						covered_from = i + 2;
+						if (L1 >= L && 4 * ((int)L1 - (int)L) + ((int)(31 - __clz((int)D)) - (int)(31 - __clz((int)D1))) > 2) {
+							// the next position's match is clearly better: literal here, go on from there
+							i++;
+							L = L1; D = D1;
+							have = true;
+							continue;
+						}
+					}
+					// positions covered by the match inherit it at the same distance; 'mend' (end of
+					// the match at that distance) only ever moves forward, so the extension of the
+					// inherited matches (needed when L was capped at 258) is amortised O(1)
+					u32 stop = i + L < i_end ? i + L : i_end;
+					if (b0 + stop > pend) stop = pend - b0;
+					u32 mend = p + L;
+					for (u32 k = covered_from; k < stop; k++) {
+						const u32 pk = b0 + k;
+						while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - D)) mend++;
+						u32 lk = mend - pk;
+						rlen[k] = (u16)(lk >= 4 ? lk : 0);
+						roff[k] = (u16)(lk >= 4 ? D - 1 : 0);
+					}
+					i += L;
 				}
 			}
 			__syncthreads();
 			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
-			for (u32 w = warp; w < LZ_NWIN; w += LZ_WARPS) {
+			const u32 nwin = (pend - b0 + 31) >> 5;
+			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				u32 i = w * 32 + lane;
 				u32 p = b0 + i;
 				const u32 min_len = v->min_len;
-				u32 L0 = rlen[i], O0 = (roff[i] & 0x7fff) + 1;
-				bool is_match = L0 >= min_len && p < n;
-				if (is_match && P.lazy && i + 1 < LZ_BATCH) {
+				u32 L0 = p < pend ? rlen[i] : 0, O0 = p < pend ? (roff[i] & 0x7fff) + 1 : 1;
+				bool is_match = L0 >= min_len && p < pend;
+				if (is_match && P.lazy && p + 1 < pend) {
 					u32 L1 = rlen[i + 1], O1 = (roff[i + 1] & 0x7fff) + 1;
 					// ref: deflate_compress.c:2722-2725 -- prefer the next position's match if clearly better
 					if (L1 >= L0 && L0 < (u32)P.nice &&
@@ -579,42 +637,57 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						is_match = false;
 				}
 				u32 step = is_match ? L0 : 1;
-				if (is_match) roff[i] |= 0x8000;	// decision flag; readers mask it off
+				// decision flag in the top bit; the neighbour that reads roff[i] for its lazy test
+				// masks it off, and it only reads -- the flag is published after this warp's reads
+				__syncwarp();
+				if (is_match) roff[i] = (u16)((O0 - 1) | 0x8000);
 				u32 j = lane + step;
-				u32 jk[5];
 #pragma unroll
 				for (int k = 0; k < 5; k++) {
-					jk[k] = j;
 					u32 t = __shfl_sync(LDB_FULL_MASK, j, j & 31);
 					if (j < 32) j = t;
 				}
-				exitt[i] = (u16)j;
+				if (p < pend) exitt[i] = (u16)j;
 			}
 			__syncthreads();
-			// (e2) chain the windows (one thread)
-			if (tid == 0) {
+			// (e2) chain the windows: warp 0 walks them in order; the 32 exits of a window sit in
+			// one register per lane (coalesced load, issued ahead of the dependent chain) and the
+			// step is a shuffle
+			if (warp == 0) {
 				u32 e = v->parse_entry;
-				for (u32 w = 0; w < LZ_NWIN; w++) {
-					u32 base = b0 + w * 32;
-					if (e >= base && e < base + 32 && e < bend) {
-						entryt[w] = (u8)(e - base);
-						e = base + exitt[w * 32 + (e - base)];
-					} else {
-						entryt[w] = 0xff;
+				for (u32 w0 = 0; w0 < nwin; w0 += 8) {
+					u32 ex[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						u32 w = w0 + k;
+						u32 i = w * 32 + lane;
+						ex[k] = (w < nwin && b0 + i < pend) ? exitt[i] : (lane + 1);
+					}
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						u32 w = w0 + k;
+						if (w < nwin) {
+							u32 base = b0 + w * 32;
+							bool inside = e >= base && e < base + 32 && e < pend;
+							u32 x = __shfl_sync(LDB_FULL_MASK, ex[k], (e - base) & 31);
+							if (lane == 0) entryt[w] = inside ? (u8)(e - base) : 0xff;
+							if (inside) e = base + x;
+						}
 					}
 				}
-				if (e < bend) e = bend;	// only when bend == n cut a window short
-				v->parse_entry = e;
+				if (e < pend) e = pend;
+				if (lane == 0) v->parse_entry = e;
 			}
 			__syncthreads();
 			// (e3) visited sets per window
-			for (u32 w = warp; w < LZ_NWIN; w += LZ_WARPS) {
+			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				u32 i = w * 32 + lane;
 				u32 e = entryt[w];
 				u32 V = 0;
 				if (e != 0xff) {
-					bool is_match = (roff[i] & 0x8000) != 0;
-					u32 step = is_match ? rlen[i] : 1;
+					bool in_pass = b0 + i < pend;
+					u32 ro = in_pass ? roff[i] : 0;
+					u32 step = (ro & 0x8000) ? rlen[i] : 1;
 					u32 j = lane + step;
 					u32 jk[5];
 #pragma unroll
@@ -629,68 +702,53 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						u32 contrib = (((V >> lane) & 1) && jk[k] < 32) ? (1u << jk[k]) : 0;
 						V |= __reduce_or_sync(LDB_FULL_MASK, contrib);
 					}
-					// positions at or beyond the end of the input are not tokens
+					// positions at or beyond the end of the pass are not tokens of this block
 					const u32 wbase = b0 + w * 32;
-					if (wbase + 32 > n) V &= n > wbase ? ((1u << (n - wbase)) - 1) : 0;
+					if (wbase + 32 > pend) V &= pend > wbase ? ((1u << (pend - wbase)) - 1) : 0;
 				}
 				if (lane == 0) vis[w] = V;
 			}
 			__syncthreads();
 			// (e4) token offsets (exclusive scan over windows) by warp 0
 			if (warp == 0) {
-				u32 cnt[4], s = 0;
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					cnt[k] = __popc(vis[lane * 4 + k]);
-					s += cnt[k];
+				u32 run = 0;
+				for (u32 w0 = 0; w0 < nwin; w0 += 32) {
+					u32 w = w0 + lane;
+					u32 c = w < nwin ? (u32)__popc(vis[w]) : 0;
+					u32 incl = c;
+					for (int o2 = 1; o2 < 32; o2 <<= 1) {
+						u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
+						if (lane >= (u32)o2) incl += t;
+					}
+					if (w < nwin) tokoff[w] = run + incl - c;
+					run += __shfl_sync(LDB_FULL_MASK, incl, 31);
 				}
-				u32 incl = s;
-				for (int o2 = 1; o2 < 32; o2 <<= 1) {
-					u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
-					if (lane >= (u32)o2) incl += t;
-				}
-				u32 run = incl - s;
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					tokoff[lane * 4 + k] = run;
-					run += cnt[k];
-				}
-				if (lane == 31) tokoff[LZ_NWIN] = incl;
+				if (lane == 0) tokoff[LZ_NWIN] = run;
 			}
 			__syncthreads();
 			// (e5) emit tokens + histograms
-			{
-				const u32 tbase = v->tok_count;
-				for (u32 w = warp; w < LZ_NWIN; w += LZ_WARPS) {
-					u32 V = vis[w];
-					if (!V) continue;
-					u32 i = w * 32 + lane;
-					if ((V >> lane) & 1) {
-						u32 idx = tbase + tokoff[w] + __popc(V & ((1u << lane) - 1));
-						u32 ro = roff[i];
-						if (ro & 0x8000) {
-							u32 len = rlen[i], off = (ro & 0x7fff) + 1;
-							tokbuf[idx] = 0x80000000u | ((len - 3) << 15) | (off - 1);
-							atomicAdd(&freq[257 + lz_len_slot(len)], 1u);
-							atomicAdd(&freq[288 + lz_off_slot(off)], 1u);
-						} else {
-							u32 b = lz_ld8(ring, b0 + i);
-							tokbuf[idx] = b;
-							atomicAdd(&freq[b], 1u);
-						}
+			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
+				u32 V = vis[w];
+				if (!V) continue;
+				u32 i = w * 32 + lane;
+				if ((V >> lane) & 1) {
+					u32 idx = tokoff[w] + __popc(V & ((1u << lane) - 1));
+					u32 ro = roff[i];
+					if (ro & 0x8000) {
+						u32 len = rlen[i], off = (ro & 0x7fff) + 1;
+						tokbuf[idx] = 0x80000000u | ((len - 3) << 15) | (off - 1);
+						atomicAdd(&freq[257 + lz_len_slot(len)], 1u);
+						atomicAdd(&freq[288 + lz_off_slot(off)], 1u);
+					} else {
+						u32 bv = lz_ld8(ring, b0 + i);
+						tokbuf[idx] = bv;
+						atomicAdd(&freq[bv], 1u);
 					}
 				}
 			}
 			__syncthreads();
-			if (tid == 0) v->tok_count += tokoff[LZ_NWIN];
+			const u32 ntok = tokoff[LZ_NWIN];
 			__syncthreads();
-
-			// ---- block boundary? ---------------------------------------------------------
-			const u32 pe = v->parse_entry;
-			const bool last = bend >= n;
-			if (!(last || pe >= next_block_cut)) continue;
-			const u32 block_end = last ? n : pe;	// input covered by this block: [block_begin, block_end)
-			const u32 ntok = v->tok_count;
 
 			// ======================= block flush =========================================
 			if (tid == 0) freq[256] = 1;
@@ -947,23 +1005,23 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
 						if (lane >= (u32)o2) incl += t;
 					}
-					if (lane == 31) tokoff[warp] = incl;
+					if (lane == 31) escan[warp] = incl;
 					__syncthreads();
 					if (warp == 0) {
-						u32 x = lane < LZ_WARPS ? tokoff[lane] : 0;
+						u32 x = lane < LZ_WARPS ? escan[lane] : 0;
 						u32 xi = x;
 						for (int o2 = 1; o2 < 32; o2 <<= 1) {
 							u32 t = __shfl_up_sync(LDB_FULL_MASK, xi, o2);
 							if (lane >= (u32)o2) xi += t;
 						}
-						if (lane < LZ_WARPS) tokoff[32 + lane] = xi - x;
-						if (lane == LZ_WARPS - 1) tokoff[64] = xi;
+						if (lane < LZ_WARPS) escan[32 + lane] = xi - x;
+						if (lane == LZ_WARPS - 1) escan[64] = xi;
 					}
 					__syncthreads();
-					u32 bitpos = rel + tokoff[32 + warp] + (incl - mine);
+					u32 bitpos = rel + escan[32 + warp] + (incl - mine);
 					lz_stage_or(stage, bitpos, myval[0], mybits[0]);
 					lz_stage_or(stage, bitpos + mybits[0], myval[1], mybits[1]);
-					const u32 round_bits = tokoff[64];
+					const u32 round_bits = escan[64];
 					__syncthreads();
 					rel += round_bits;
 					// flush complete words, keep the partial one as the new stage[0]
@@ -986,10 +1044,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			__syncthreads();
 			if (tid == 0) v->carry = stage[0];
 			// ---- next block ------------------------------------------------------------
-			block_begin = block_end;
-			next_block_cut = (n - block_begin < LZ_BLOCK_IN + LZ_MIN_BLOCK) ? n : block_begin + LZ_BLOCK_IN;
 			for (u32 i = tid; i < 320; i += LZ_THREADS) freq[i] = 0;
-			if (tid == 0) v->tok_count = 0;
 			__syncthreads();
 		}
 		__syncthreads();
@@ -1026,7 +1081,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 
 size_t ldb_deflate_scratch_bytes(const ldb_launch_cfg &cfg)
 {
-	return (size_t)ldb_deflate_grid(cfg) * LZ_TOKCAP * sizeof(u32) + 256;
+	return (size_t)ldb_deflate_grid(cfg) * LZ_GS_BYTES + 256;
 }
 
 static int ldb_launch_deflate_lz(const ldb_deflate_args &a, const ldb_launch_cfg &cfg, void *stream)
@@ -1037,7 +1092,7 @@ static int ldb_launch_deflate_lz(const ldb_deflate_args &a, const ldb_launch_cfg
 		attr_set = true;
 	}
 	ldb_deflate_args b = a;
-	b.work_counter = (u32 *)(a.scratch + (size_t)ldb_deflate_grid(cfg) * LZ_TOKCAP * sizeof(u32));
+	b.work_counter = (u32 *)(a.scratch + (size_t)ldb_deflate_grid(cfg) * LZ_GS_BYTES);
 	LDB_CUDA_CHECK_RET(cudaMemsetAsync(b.work_counter, 0, sizeof(u32), (cudaStream_t)stream));
 	size_t blocks = a.n < (size_t)ldb_deflate_grid(cfg) ? a.n : (size_t)ldb_deflate_grid(cfg);
 	LDB_LAUNCH(ldb_deflate_lz_kernel, dim3((unsigned)blocks), dim3(LZ_THREADS), LZ_SM_BYTES, (cudaStream_t)stream, b);

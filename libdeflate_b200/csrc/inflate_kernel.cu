@@ -56,7 +56,7 @@
 #ifndef INF_LSUB_SM
 #define INF_LSUB_SM   32		// litlen subtable entries kept in shared memory
 #endif
-#define INF_LSUB_CAP  1024		// total litlen subtable capacity (rest in global scratch)
+#define INF_LSUB_CAP  2048		// total litlen subtable capacity (rest in global scratch)
 #ifndef INF_OB
 #define INF_OB        5			// main offset table bits
 #endif
@@ -64,7 +64,7 @@
 #ifndef INF_OSUB_SM
 #define INF_OSUB_SM   32
 #endif
-#define INF_OSUB_CAP  1024
+#define INF_OSUB_CAP  2048		// a 5-bit root can need a 1024-entry subtable plus smaller ones
 #define INF_L_ENTRIES (INF_LMAIN + INF_LSUB_SM)		// 640 u16 per lane
 #define INF_O_ENTRIES (INF_OMAIN + INF_OSUB_SM)		// 128 u16 per lane
 #define INF_L_WORDS   (INF_L_ENTRIES / 2)		// 320 words per lane
@@ -647,7 +647,7 @@ __device__ bool inf_build_table(const u32 (&mylen)[NROWS], u8 *sm, u32 tab_off, 
 		u32 p = lane * per_lane + j;
 		u32 sb = subbits[p];
 		if (sb) {
-			u32 e = (IS_LITLEN ? LE_SUB_FLAG : OE_SUB_FLAG) | (start << 4) | sb;
+			u32 e = (IS_LITLEN ? LE_SUB_FLAG : OE_SUB_FLAG) | ((start >> 1) << 4) | sb;	// starts are even (sizes >= 2)
 			tab[tab_idx(p, owner)] = (u16)e;
 			start += 1u << sb;
 		}
@@ -663,7 +663,7 @@ __device__ bool inf_build_table(const u32 (&mylen)[NROWS], u8 *sm, u32 tab_off, 
 		u32 sym = r * 32 + lane;
 		u32 prefix = rev & ((1u << MAINBITS) - 1);
 		u32 pe = tab[tab_idx(prefix, owner)];
-		u32 sstart = (pe >> 4) & 0x3ff;
+		u32 sstart = ((pe >> 4) & 0x3ff) << 1;
 		u32 sb = pe & 15;
 		u32 e = make_entry(sym, l - MAINBITS);
 		for (u32 i = rev >> MAINBITS; i < (1u << sb); i += 1u << (l - MAINBITS)) {
@@ -698,7 +698,7 @@ __device__ __forceinline__ int inf_decode_litlen(inf_lane &s, const u8 *sm, cons
 	}
 	u32 e = ltab[tab_idx(bits & (INF_LMAIN - 1), lane)];
 	if (e >= LE_SUB_FLAG) {
-		u32 sstart = (e >> 4) & 0x3ff;
+		u32 sstart = ((e >> 4) & 0x3ff) << 1;
 		u32 sb = e & 15;
 		bits >>= INF_LB;
 		s.bitpos += INF_LB;
@@ -741,7 +741,7 @@ __device__ __forceinline__ int inf_decode_offset(inf_lane &s, const u8 *sm, cons
 	u32 bits = inf_peek(s);
 	u32 oe = otab[tab_idx(bits & (INF_OMAIN - 1), lane)];
 	if (oe & OE_SUB_FLAG) {
-		u32 sstart = (oe >> 4) & 0x3ff;
+		u32 sstart = ((oe >> 4) & 0x3ff) << 1;
 		u32 sb = oe & 15;
 		bits >>= INF_OB;
 		s.bitpos += INF_OB;
