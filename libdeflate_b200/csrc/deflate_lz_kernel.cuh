@@ -36,16 +36,17 @@
 
 #define LZ_THREADS   512
 #define LZ_WARPS     (LZ_THREADS / 32)
-#define LZ_PASS      32768			// positions matched + parsed per pass = one DEFLATE block
+#define LZ_PASS      16384			// positions matched + parsed per pass
+#define LZ_BLOCK_PASSES 2			// passes per DEFLATE block (32 KiB of input)
 #define LZ_NWIN      (LZ_PASS / 32)
-#define LZ_RUN       (LZ_PASS / LZ_THREADS)	// consecutive positions owned by one searcher thread
+#define LZ_SEARCHERS (LZ_THREADS - 32)		// warp 0 inserts the next pass while the others search
 #define LZ_SEG       16384			// largest single TMA load
 #define LZ_RING      65536
 #define LZ_HASH_BITS 13
 #define LZ_WIN       32768
 #define LZ_LOOKAHEAD 512			// bytes past the pass kept in the ring (>= 258 + 8)
 #define LZ_MAX_DIST  (LZ_WIN - LZ_LOOKAHEAD)	// the oldest LOOKAHEAD bytes of the window are overwritten
-#define LZ_TOKCAP    (LZ_PASS + 64)
+#define LZ_TOKCAP    (LZ_BLOCK_PASSES * LZ_PASS + 64)
 #define LZ_STAGE_WORDS 2048			// 8 KiB emission staging
 #define LZ_EMIT_ROUND  1024			// tokens per emission round (<= 48 bits each)
 
@@ -346,14 +347,24 @@ __device__ __forceinline__ void lz_insert_pass(const u8 *ring, u16 *head, u16 *n
 		const u32 p = base + lane;
 		const bool valid = p < pend && p + 4 <= n;
 		const u32 h = valid ? lz_hash(lz_ld32(ring, p)) : 0;
-		const u32 m = __match_any_sync(LDB_FULL_MASK, valid ? h : (0x10000u | lane));
 		const u32 old_head = valid ? head[h] : 0;
 		__syncwarp();
-		if (valid) {
-			const u32 below = m & lt;
-			const u32 pred = below ? (p - lane + (31 - __clz(below))) & 0xffff : old_head;
-			nextt[p & 0xffff] = (u16)pred;
-			if ((m >> lane) == 1) head[h] = (u16)p;	// highest lane of the group
+		// optimistic step: everybody publishes itself as the new head; if every lane reads its
+		// own position back, all 32 hashes are distinct and the links are simply the old heads
+		if (valid) head[h] = (u16)p;
+		__syncwarp();
+		const bool lost = valid && head[h] != (u16)p;
+		if (!__any_sync(LDB_FULL_MASK, lost)) {
+			if (valid) nextt[p & 0xffff] = (u16)old_head;
+		} else {
+			// some lanes share a hash: order them (rare; __match_any_sync is slow)
+			const u32 m = __match_any_sync(LDB_FULL_MASK, valid ? h : (0x10000u | lane));
+			if (valid) {
+				const u32 below = m & lt;
+				const u32 pred = below ? (p - lane + (31 - __clz(below))) & 0xffff : old_head;
+				nextt[p & 0xffff] = (u16)pred;
+				if ((m >> lane) == 1) head[h] = (u16)p;	// highest lane of the group owns the head
+			}
 		}
 		__syncwarp();
 	}
@@ -520,17 +531,20 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		__syncthreads();
 
 		u32 loaded_end = 0;
+		u32 block_begin = 0;
+		u32 pass_in_block = 0;
 
 		for (u32 b0 = 0; b0 < n; b0 += LZ_PASS) {
 			const u32 pend = b0 + LZ_PASS < n ? b0 + LZ_PASS : n;
-			const u32 block_begin = b0, block_end = pend;
 			const bool last = pend >= n;
-			// (a) window staging by the TMA engine: the ring holds [b0 - MAX_DIST, pend + LOOKAHEAD)
+			// (a) window staging by the TMA engine, one pass ahead: searching this pass needs
+			// [b0 - MAX_DIST, pend + LOOKAHEAD), inserting the next one (concurrently) needs the
+			// bytes up to pend + PASS + 3.  The ring then still holds everything back to
+			// b0 - 32768 + 16, i.e. the whole MAX_DIST window.
 			{
-				const u32 want = pend + LZ_LOOKAHEAD < n ? pend + LZ_LOOKAHEAD : n;
+				const u32 want = pend + LZ_PASS + 16 < n ? pend + LZ_PASS + 16 : n;
 				while (loaded_end < want) {
-					// a segment must not wrap around the ring
-					u32 room = LZ_RING - (loaded_end & (LZ_RING - 1));
+					u32 room = LZ_RING - (loaded_end & (LZ_RING - 1));	// a segment must not wrap
 					u32 to = loaded_end + (room < LZ_SEG ? room : LZ_SEG);
 					if (to > want) to = want;
 					lz_load_segment(sm, v, in, loaded_end, to);
@@ -553,71 +567,77 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					for (int k = 0; k < 8; k++) cnt += __popc(v->used_lits[k]);
 					v->min_len = n < 512 ? 4 : lz_choose_min_len(cnt, (u32)P.depth);
 				}
+				if (warp == 0) lz_insert_pass(ring, head, nextt, 0, pend, n, lane);
 				__syncthreads();
 			}
-			// (b) ordered chain insertion of the whole pass (one warp)
-			if (warp == 0) lz_insert_pass(ring, head, nextt, b0, pend, n, lane);
-			__syncthreads();
-			// (c) guided search.  Every thread owns a run of LZ_RUN consecutive positions and
-			// walks it like the reference's lazy parser (deflate_compress.c:2605-2808): search
-			// where a token could start, look one position ahead, then skip the positions the
-			// chosen match covers (they inherit the match, one byte shorter each).  Every
-			// position still gets a (length, distance) so that the exact, parallel parse below
-			// can start a token anywhere.
-			{
+			// (b) warp 0 inserts the NEXT pass into the hash chains (ordered) while the other 15
+			// warps search THIS pass.  next[] has a slot per position mod 65536 and a pass is
+			// 16 Ki positions, so the slots written now belong to positions 48..64 Ki back --
+			// outside every window -- and the searchers only follow links of older positions.
+			if (warp == 0) {
+				if (!last) lz_insert_pass(ring, head, nextt, pend, pend + LZ_PASS < n ? pend + LZ_PASS : n, n, lane);
+			} else {
+				// (c) guided search.  Every searcher owns a run of consecutive positions and walks
+				// it like the reference's lazy parser (deflate_compress.c:2605-2808): search where
+				// a token could start, look one position ahead, then skip the positions the
+				// chosen match covers (they inherit it at the same distance).  Every position
+				// still gets a (length, distance), so the exact parallel parse below can start a
+				// token anywhere.  One search call site per loop trip keeps the warp converged.
 				const u32 min_len = v->min_len;
-				const u32 i_begin = tid * LZ_RUN;
-				const u32 i_end = i_begin + LZ_RUN;
-				u32 i = i_begin;
-				u32 L = 0, D = 0;
-				bool have = false;
-				while (i < i_end) {
+				const u32 st = tid - 32;
+				const u32 i_end = ((st + 1) * LZ_PASS) / LZ_SEARCHERS;
+				u32 i = (st * LZ_PASS) / LZ_SEARCHERS;
+				u32 pL = 0, pD = 0;		// pending match at position i-1 (lazy evaluation in progress)
+				bool pending = false;
+				while (i < i_end && b0 + i < pend) {
 					const u32 p = b0 + i;
-					if (p >= pend) break;
-					if (p + 4 > n) {
-						rlen[i] = 0;
-						roff[i] = 0;
-						i++;
-						have = false;
-						continue;
+					u32 L = 0, D = 0;
+					if (p + 4 <= n) {
+						if (pending) { L = pL - 1 >= 4 ? pL - 1 : 0; D = pD; }
+						lz_search(ring, nextt, p, n, pending ? (P.depth >> 1) : P.depth, (u32)P.nice, L, D);
 					}
-					if (!have) {
-						L = 0; D = 0;
-						lz_search(ring, nextt, p, n, P.depth, (u32)P.nice, L, D);
-						rlen[i] = (u16)L;
-						roff[i] = (u16)(L ? D - 1 : 0);
-					}
-					have = false;
-					if (L < min_len) { i++; continue; }
-					u32 covered_from = i + 1;	// first position whose result is still to be written
-					if (P.lazy && L < (u32)P.nice && i + 1 < i_end && p + 1 + 4 <= n && p + 1 < pend) {
-						u32 L1 = L - 1 >= 4 ? L - 1 : 0, D1 = D;
-						lz_search(ring, nextt, p + 1, n, P.depth >> 1, (u32)P.nice, L1, D1);
-						rlen[i + 1] = (u16)L1;
-						roff[i + 1] = (u16)(L1 ? D1 - 1 : 0);
-						covered_from = i + 2;
-						if (L1 >= L && 4 * ((int)L1 - (int)L) + ((int)(31 - __clz((int)D)) - (int)(31 - __clz((int)D1))) > 2) {
-							// the next position's match is clearly better: literal here, go on from there
-							i++;
-							L = L1; D = D1;
-							have = true;
-							continue;
+					rlen[i] = (u16)L;
+					roff[i] = (u16)(L ? D - 1 : 0);
+					u32 mpos, mL, mD;	// match to accept this trip (mL == 0: none)
+					if (pending) {
+						if (L >= pL && 4 * ((int)L - (int)pL) + ((int)(31 - __clz((int)pD)) - (int)(31 - __clz((int)D))) > 2) {
+							// the lookahead match is clearly better: literal at i-1, keep looking
+							// ahead from i unless it is long enough to take at once
+							mpos = i; mL = L >= (u32)P.nice ? L : 0; mD = D;
+							if (!mL) { pL = L; pD = D; }
+							pending = mL == 0;
+						} else {
+							mpos = i - 1; mL = pL; mD = pD;
+							pending = false;
 						}
+					} else if (L >= min_len) {
+						if (P.lazy && L < (u32)P.nice && i + 1 < i_end && b0 + i + 1 < pend) {
+							pending = true; pL = L; pD = D;
+							mpos = i; mL = 0; mD = 0;
+						} else {
+							mpos = i; mL = L; mD = D;
+						}
+					} else {
+						mpos = i; mL = 0; mD = 0;
 					}
-					// positions covered by the match inherit it at the same distance; 'mend' (end of
-					// the match at that distance) only ever moves forward, so the extension of the
-					// inherited matches (needed when L was capped at 258) is amortised O(1)
-					u32 stop = i + L < i_end ? i + L : i_end;
-					if (b0 + stop > pend) stop = pend - b0;
-					u32 mend = p + L;
-					for (u32 k = covered_from; k < stop; k++) {
-						const u32 pk = b0 + k;
-						while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - D)) mend++;
-						u32 lk = mend - pk;
-						rlen[k] = (u16)(lk >= 4 ? lk : 0);
-						roff[k] = (u16)(lk >= 4 ? D - 1 : 0);
+					if (mL) {
+						// positions covered by the accepted match inherit it at the same distance;
+						// 'mend' (end of the match at that distance) only moves forward, so extending
+						// the inherited matches (needed when the match was capped at 258) is O(1) amortised
+						u32 stop = mpos + mL < i_end ? mpos + mL : i_end;
+						if (b0 + stop > pend) stop = pend - b0;
+						u32 mend = b0 + mpos + mL;
+						for (u32 k = i + 1; k < stop; k++) {
+							const u32 pk = b0 + k;
+							while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - mD)) mend++;
+							u32 lk = mend - pk;
+							rlen[k] = (u16)(lk >= 4 ? lk : 0);
+							roff[k] = (u16)(lk >= 4 ? mD - 1 : 0);
+						}
+						i = mpos + mL;
+					} else {
+						i++;
 					}
-					i += L;
 				}
 			}
 			__syncthreads();
@@ -727,12 +747,13 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			}
 			__syncthreads();
 			// (e5) emit tokens + histograms
+			const u32 tbase = v->tok_count;
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				u32 V = vis[w];
 				if (!V) continue;
 				u32 i = w * 32 + lane;
 				if ((V >> lane) & 1) {
-					u32 idx = tokoff[w] + __popc(V & ((1u << lane) - 1));
+					u32 idx = tbase + tokoff[w] + __popc(V & ((1u << lane) - 1));
 					u32 ro = roff[i];
 					if (ro & 0x8000) {
 						u32 len = rlen[i], off = (ro & 0x7fff) + 1;
@@ -747,8 +768,14 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				}
 			}
 			__syncthreads();
-			const u32 ntok = tokoff[LZ_NWIN];
+			if (tid == 0) v->tok_count = tbase + tokoff[LZ_NWIN];
 			__syncthreads();
+			// ---- block boundary: every LZ_BLOCK_PASSES passes, or at the end of the input --------
+			pass_in_block++;
+			if (!(last || pass_in_block == LZ_BLOCK_PASSES)) continue;
+			pass_in_block = 0;
+			const u32 block_end = pend;
+			const u32 ntok = v->tok_count;
 
 			// ======================= block flush =========================================
 			if (tid == 0) freq[256] = 1;
@@ -1044,7 +1071,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			__syncthreads();
 			if (tid == 0) v->carry = stage[0];
 			// ---- next block ------------------------------------------------------------
+			block_begin = block_end;
 			for (u32 i = tid; i < 320; i += LZ_THREADS) freq[i] = 0;
+			if (tid == 0) v->tok_count = 0;
 			__syncthreads();
 		}
 		__syncthreads();
