@@ -40,6 +40,9 @@
 #define LZ_BLOCK_PASSES 2			// passes per DEFLATE block (32 KiB of input)
 #define LZ_NWIN      (LZ_PASS / 32)
 #define LZ_SEARCHERS (LZ_THREADS - 32)		// warp 0 inserts the next pass while the others search
+#ifndef LZ_RUN
+#define LZ_RUN       16			// consecutive positions per dynamically assigned search run
+#endif
 #define LZ_SEG       16384			// largest single TMA load
 #define LZ_RING      65536
 #define LZ_HASH_BITS 13
@@ -81,6 +84,7 @@ struct lz_vars {
 	u32 cost_dyn, cost_static, extra_bits;
 	u32 hlit, hdist, hclen;
 	u32 n_items;
+	u32 run_counter;	// next unassigned search run of the current pass
 	u32 min_len;		// shortest match worth taking (depends on the alphabet size)
 	u32 used_lits[8];	// 256-bit set of byte values seen in the first 4 KiB
 	u32 carry;		// partial output word at bit position obit (persists between flushes)
@@ -537,6 +541,8 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		for (u32 b0 = 0; b0 < n; b0 += LZ_PASS) {
 			const u32 pend = b0 + LZ_PASS < n ? b0 + LZ_PASS : n;
 			const bool last = pend >= n;
+			if (tid == 0) v->run_counter = 0;
+			__syncthreads();
 			// (a) window staging by the TMA engine, one pass ahead: searching this pass needs
 			// [b0 - MAX_DIST, pend + LOOKAHEAD), inserting the next one (concurrently) needs the
 			// bytes up to pend + PASS + 3.  The ring then still holds everything back to
@@ -584,12 +590,19 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// still gets a (length, distance), so the exact parallel parse below can start a
 				// token anywhere.  One search call site per loop trip keeps the warp converged.
 				const u32 min_len = v->min_len;
-				const u32 st = tid - 32;
-				const u32 i_end = ((st + 1) * LZ_PASS) / LZ_SEARCHERS;
-				u32 i = (st * LZ_PASS) / LZ_SEARCHERS;
+				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
+				// (long matches, few searches) take more of them, which keeps the warp busy
+				u32 i = 0, i_end = 0;
 				u32 pL = 0, pD = 0;		// pending match at position i-1 (lazy evaluation in progress)
 				bool pending = false;
-				while (i < i_end && b0 + i < pend) {
+				for (;;) {
+					if (i >= i_end || b0 + i >= pend) {
+						const u32 r = atomicAdd(&v->run_counter, 1u);
+						i = r * LZ_RUN;
+						if (b0 + i >= pend || i >= LZ_PASS) break;
+						i_end = i + LZ_RUN;
+						pending = false;
+					}
 					const u32 p = b0 + i;
 					u32 L = 0, D = 0;
 					if (p + 4 <= n) {
@@ -755,8 +768,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				if ((V >> lane) & 1) {
 					u32 idx = tbase + tokoff[w] + __popc(V & ((1u << lane) - 1));
 					u32 ro = roff[i];
-					if (ro & 0x8000) {
-						u32 len = rlen[i], off = (ro & 0x7fff) + 1;
+					u32 len = rlen[i], off = (ro & 0x7fff) + 1;
+					// (a match that does not fit the data would be a bug upstream; never emit one)
+					if ((ro & 0x8000) && len >= 3 && len <= 258 && off <= b0 + i && b0 + i + len <= n) {
 						tokbuf[idx] = 0x80000000u | ((len - 3) << 15) | (off - 1);
 						atomicAdd(&freq[257 + lz_len_slot(len)], 1u);
 						atomicAdd(&freq[288 + lz_off_slot(off)], 1u);

@@ -132,6 +132,7 @@ struct libdeflate_b200_ctx {
 	ldb_buf h_pinned;		// pinned host staging
 	u64 launches;
 	cudaEvent_t ev_start, ev_stop;
+	cudaStream_t stream_h2d, stream_d2h;	// copy streams of the pipelined host-buffer path
 	// optional per-kernel stopwatch (libdeflate_b200_ctx_set_profiling)
 	int profiling;
 	std::vector<ldb_prof_rec> *prof;
@@ -206,6 +207,10 @@ extern "C" struct libdeflate_b200_ctx *libdeflate_b200_ctx_create(int device)
 	for (int k = 0; k < LDB_KERNEL_KINDS; k++) { ctx->prof_ms[k] = 0; ctx->prof_n[k] = 0; }
 	ctx->ev_start = nullptr;
 	ctx->ev_stop = nullptr;
+	ctx->stream_h2d = nullptr;
+	ctx->stream_d2h = nullptr;
+	cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking);
 	cudaEventCreate(&ctx->ev_start);
 	cudaEventCreate(&ctx->ev_stop);
 	ldb_crc_tables *h = new ldb_crc_tables();
@@ -232,6 +237,8 @@ extern "C" void libdeflate_b200_ctx_destroy(struct libdeflate_b200_ctx *ctx)
 		for (auto &r : *ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
 		delete ctx->prof;
 	}
+	if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
+	if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
 	if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
 	if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
 	cudaFree(ctx->d_crc_tables);
@@ -501,9 +508,9 @@ struct staged_batch {
 // Lays out n buffers of the given sizes in a device slab (16-byte aligned each, or
 // mirroring the host span when compact) and uploads pointer + size arrays.
 static int stage_layout(libdeflate_b200_ctx *ctx, ldb_buf &slab, const void *const *h_ptrs, const size_t *h_sizes,
-			size_t n, bool copy_in, u8 *param_base_d, u8 *param_base_h, staged_batch *sb)
+			size_t n, bool copy_in, bool exact, u8 *param_base_d, u8 *param_base_h, staged_batch *sb)
 {
-	host_span sp = span_of(h_ptrs, h_sizes, n, !copy_in);
+	host_span sp = span_of(h_ptrs, h_sizes, n, exact);
 	sb->compact = sp.compact;
 	sb->offsets = (size_t *)malloc(n * sizeof(size_t) + 8);
 	size_t total = 0;
@@ -550,6 +557,59 @@ static int stage_layout(libdeflate_b200_ctx *ctx, ldb_buf &slab, const void *con
 
 static size_t param_block_bytes(size_t n) { return align_up(n * sizeof(void *), 256) + align_up(n * sizeof(size_t), 256); }
 
+
+// ---- pipelined host-buffer path ---------------------------------------------------------------
+// Large batches whose host buffers sit in address order inside one span are processed in
+// sub-batches: H2D of sub-batch k+1 (copy stream), kernels of sub-batch k (compute stream) and
+// D2H of sub-batch k-1 (second copy stream) overlap, PCIe runs full duplex.
+#define LDB_PIPE_MIN_CHUNKS 2048
+#define LDB_PIPE_MAX_STAGES 16
+
+static bool host_ordered(const void *const *ptrs, const size_t *sizes, size_t n)
+{
+	for (size_t i = 0; i + 1 < n; i++) {
+		if (!ptrs[i] || !ptrs[i + 1]) return false;
+		if ((const u8 *)ptrs[i] + sizes[i] > (const u8 *)ptrs[i + 1]) return false;
+	}
+	return n && ptrs[n - 1];
+}
+
+static bool pipeline_eligible(const libdeflate_b200_ctx *ctx, const void *const *h_in, const size_t *in_sz,
+			      const void *const *h_out, const size_t *out_sz, size_t n)
+{
+	if (n < LDB_PIPE_MIN_CHUNKS || !ctx->stream_h2d || !ctx->stream_d2h) return false;
+	if (getenv("LIBDEFLATE_B200_NO_PIPELINE")) return false;
+	host_span a = span_of(h_in, in_sz, n, false), b = span_of(h_out, out_sz, n, true);
+	return a.compact && b.compact && host_ordered(h_in, in_sz, n) && host_ordered(h_out, out_sz, n);
+}
+
+struct pipe_events {
+	cudaEvent_t in[LDB_PIPE_MAX_STAGES], done[LDB_PIPE_MAX_STAGES];
+	int n;
+};
+static int pipe_events_create(pipe_events *e, int n)
+{
+	e->n = 0;
+	for (int i = 0; i < n; i++) {
+		LDB_CUDA_CHECK_RET(cudaEventCreateWithFlags(&e->in[i], cudaEventDisableTiming));
+		LDB_CUDA_CHECK_RET(cudaEventCreateWithFlags(&e->done[i], cudaEventDisableTiming));
+		e->n = i + 1;
+	}
+	return 0;
+}
+static void pipe_events_destroy(pipe_events *e)
+{
+	for (int i = 0; i < e->n; i++) { cudaEventDestroy(e->in[i]); cudaEventDestroy(e->done[i]); }
+}
+static size_t pipe_stages(size_t n, size_t total_bytes)
+{
+	size_t s = total_bytes / ((size_t)256 << 20);
+	if (s < 2) s = 2;
+	if (s > LDB_PIPE_MAX_STAGES) s = LDB_PIPE_MAX_STAGES;
+	if (s > n / 256) s = n / 256 ? n / 256 : 1;
+	return s;
+}
+
 extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
 						      const void *const *h_in, const size_t *h_in_nbytes,
 						      void *const *h_out, const size_t *h_out_avail,
@@ -567,16 +627,42 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 	u8 *hparam = (u8 *)malloc(res_off + res_bytes);
 	if (!hparam) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
 	u8 *dparam = (u8 *)ctx->d_params.p;
+	const bool pipelined = pipeline_eligible(ctx, h_in, h_in_nbytes, (const void *const *)h_out, h_out_avail, n);
 	staged_batch in_sb{}, out_sb{};
-	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, true, dparam, hparam, &in_sb);
-	if (!rc) rc = stage_layout(ctx, ctx->d_stage_out, (const void *const *)h_out, h_out_avail, n, false, dparam + pb, hparam + pb, &out_sb);
+	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, !pipelined, false, dparam, hparam, &in_sb);
+	if (!rc) rc = stage_layout(ctx, ctx->d_stage_out, (const void *const *)h_out, h_out_avail, n, false, true, dparam + pb, hparam + pb, &out_sb);
 	if (!rc) rc = cudaMemcpyAsync(dparam, hparam, 2 * pb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "H2D params", __FILE__, __LINE__);
 	size_t *d_ain = (size_t *)(dparam + res_off);
 	size_t *d_aout = (size_t *)(dparam + res_off + align_up(n * sizeof(size_t), 256));
 	s32 *d_res = (s32 *)(dparam + res_off + 2 * align_up(n * sizeof(size_t), 256));
-	if (!rc)
+	bool out_copied = false;
+	if (!rc && pipelined) {
+		host_span isp = span_of(h_in, h_in_nbytes, n, false), osp = span_of((const void *const *)h_out, h_out_avail, n, true);
+		const size_t imis = (uintptr_t)isp.lo & 15, omis = (uintptr_t)osp.lo & 15;
+		const size_t S = pipe_stages(n, (size_t)(isp.hi - isp.lo) + (size_t)(osp.hi - osp.lo));
+		pipe_events ev;
+		rc = pipe_events_create(&ev, (int)S);
+		for (size_t k = 0; k < S && !rc; k++) {
+			const size_t i0 = n * k / S, i1 = n * (k + 1) / S;
+			const u8 *ilo = (const u8 *)h_in[i0], *ihi = (const u8 *)h_in[i1 - 1] + h_in_nbytes[i1 - 1];
+			u8 *olo = (u8 *)h_out[i0], *ohi = (u8 *)h_out[i1 - 1] + h_out_avail[i1 - 1];
+			if (ihi > ilo) LDB_CUDA_CHECK_RET(cudaMemcpyAsync(in_sb.d_base + imis + (ilo - isp.lo), ilo, (size_t)(ihi - ilo), cudaMemcpyHostToDevice, ctx->stream_h2d));
+			LDB_CUDA_CHECK_RET(cudaEventRecord(ev.in[k], ctx->stream_h2d));
+			LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream, ev.in[k], 0));
+			rc = libdeflate_b200_decompress_batch(ctx, format, flags, (const void *const *)in_sb.d_ptrs + i0, in_sb.d_sizes + i0,
+							      (void *const *)out_sb.d_ptrs + i0, out_sb.d_sizes + i0, d_ain + i0, d_aout + i0, d_res + i0, i1 - i0);
+			if (rc) break;
+			LDB_CUDA_CHECK_RET(cudaEventRecord(ev.done[k], ctx->stream));
+			LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream_d2h, ev.done[k], 0));
+			if (ohi > olo) LDB_CUDA_CHECK_RET(cudaMemcpyAsync(olo, out_sb.d_base + omis + (olo - osp.lo), (size_t)(ohi - olo), cudaMemcpyDeviceToHost, ctx->stream_d2h));
+		}
+		if (!rc) rc = cudaStreamSynchronize(ctx->stream_d2h) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "sync d2h", __FILE__, __LINE__);
+		pipe_events_destroy(&ev);
+		out_copied = true;
+	} else if (!rc) {
 		rc = libdeflate_b200_decompress_batch(ctx, format, flags, (const void *const *)in_sb.d_ptrs, in_sb.d_sizes,
 						      (void *const *)out_sb.d_ptrs, out_sb.d_sizes, d_ain, d_aout, d_res, n);
+	}
 	u8 *hres = hparam + res_off;
 	if (!rc) rc = cudaMemcpyAsync(hres, dparam + res_off, res_bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "D2H results", __FILE__, __LINE__);
 	if (!rc) rc = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
@@ -585,7 +671,9 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 		const size_t *r_aout = (const size_t *)(hres + align_up(n * sizeof(size_t), 256));
 		const s32 *r_res = (const s32 *)(hres + 2 * align_up(n * sizeof(size_t), 256));
 		// output bytes back to the caller's buffers
-		if (out_sb.compact) {
+		if (out_copied) {
+			// done by the pipeline
+		} else if (out_sb.compact) {
 			host_span sp = span_of((const void *const *)h_out, h_out_avail, n, true);
 			size_t mis = (uintptr_t)sp.lo & 15;
 			if (sp.lo)
@@ -628,19 +716,47 @@ extern "C" int libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *c
 	u8 *hparam = (u8 *)malloc(res_off + res_bytes);
 	if (!hparam) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
 	u8 *dparam = (u8 *)ctx->d_params.p;
+	const bool pipelined = pipeline_eligible(ctx, h_in, h_in_nbytes, (const void *const *)h_out, h_out_avail, n);
 	staged_batch in_sb{}, out_sb{};
-	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, true, dparam, hparam, &in_sb);
-	if (!rc) rc = stage_layout(ctx, ctx->d_stage_out, (const void *const *)h_out, h_out_avail, n, false, dparam + pb, hparam + pb, &out_sb);
+	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, !pipelined, false, dparam, hparam, &in_sb);
+	if (!rc) rc = stage_layout(ctx, ctx->d_stage_out, (const void *const *)h_out, h_out_avail, n, false, true, dparam + pb, hparam + pb, &out_sb);
 	if (!rc) rc = cudaMemcpyAsync(dparam, hparam, 2 * pb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "H2D params", __FILE__, __LINE__);
 	size_t *d_on = (size_t *)(dparam + res_off);
-	if (!rc)
+	bool out_copied = false;
+	if (!rc && pipelined) {
+		host_span isp = span_of(h_in, h_in_nbytes, n, false), osp = span_of((const void *const *)h_out, h_out_avail, n, true);
+		const size_t imis = (uintptr_t)isp.lo & 15, omis = (uintptr_t)osp.lo & 15;
+		const size_t S = pipe_stages(n, (size_t)(isp.hi - isp.lo) + (size_t)(osp.hi - osp.lo));
+		pipe_events ev;
+		rc = pipe_events_create(&ev, (int)S);
+		for (size_t k = 0; k < S && !rc; k++) {
+			const size_t i0 = n * k / S, i1 = n * (k + 1) / S;
+			const u8 *ilo = (const u8 *)h_in[i0], *ihi = (const u8 *)h_in[i1 - 1] + h_in_nbytes[i1 - 1];
+			u8 *olo = (u8 *)h_out[i0], *ohi = (u8 *)h_out[i1 - 1] + h_out_avail[i1 - 1];
+			if (ihi > ilo) LDB_CUDA_CHECK_RET(cudaMemcpyAsync(in_sb.d_base + imis + (ilo - isp.lo), ilo, (size_t)(ihi - ilo), cudaMemcpyHostToDevice, ctx->stream_h2d));
+			LDB_CUDA_CHECK_RET(cudaEventRecord(ev.in[k], ctx->stream_h2d));
+			LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream, ev.in[k], 0));
+			rc = libdeflate_b200_compress_batch(ctx, format, level, (const void *const *)in_sb.d_ptrs + i0, in_sb.d_sizes + i0,
+							    (void *const *)out_sb.d_ptrs + i0, out_sb.d_sizes + i0, d_on + i0, i1 - i0);
+			if (rc) break;
+			LDB_CUDA_CHECK_RET(cudaEventRecord(ev.done[k], ctx->stream));
+			LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream_d2h, ev.done[k], 0));
+			if (ohi > olo) LDB_CUDA_CHECK_RET(cudaMemcpyAsync(olo, out_sb.d_base + omis + (olo - osp.lo), (size_t)(ohi - olo), cudaMemcpyDeviceToHost, ctx->stream_d2h));
+		}
+		if (!rc) rc = cudaStreamSynchronize(ctx->stream_d2h) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "sync d2h", __FILE__, __LINE__);
+		pipe_events_destroy(&ev);
+		out_copied = true;
+	} else if (!rc) {
 		rc = libdeflate_b200_compress_batch(ctx, format, level, (const void *const *)in_sb.d_ptrs, in_sb.d_sizes,
 						    (void *const *)out_sb.d_ptrs, out_sb.d_sizes, d_on, n);
+	}
 	size_t *r_on = (size_t *)(hparam + res_off);
 	if (!rc) rc = cudaMemcpyAsync(r_on, d_on, n * sizeof(size_t), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "D2H sizes", __FILE__, __LINE__);
 	if (!rc) rc = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
 	if (!rc) {
-		if (out_sb.compact) {
+		if (out_copied) {
+			// done by the pipeline
+		} else if (out_sb.compact) {
 			host_span sp = span_of((const void *const *)h_out, h_out_avail, n, true);
 			size_t mis = (uintptr_t)sp.lo & 15;
 			if (sp.lo)

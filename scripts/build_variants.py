@@ -13,14 +13,9 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    "a_r1": GEO_A + ["-DINF_LIT_ROUNDS=1"],
-    "a_r2": GEO_A + ["-DINF_LIT_ROUNDS=2"],
-    "a_r6": GEO_A + ["-DINF_LIT_ROUNDS=6"],
-    "a_c8": GEO_A + ["-DINF_COPY_CHUNK=8"],
-    "g_r4": GEO_G,
-    "c_r4": GEO_C,
-    "d_r4": GEO_D,
-    "c_r6": GEO_C + ["-DINF_LIT_ROUNDS=6", "-DINF_LIT_MIN_LANES=8"],
+    "run8": ["-DLZ_RUN=8"],
+    "run16": ["-DLZ_RUN=16"],
+    "run32": ["-DLZ_RUN=32"],
 }
 
 

@@ -150,3 +150,38 @@ def check_compress_round_trip(ctx, orc, chunks, levels=(1, 6, 9), fmts=(0, 1, 2)
         theirs = sum(s[3] for s in stats)
         assert ours <= theirs * max_ratio_vs_ref, ("ratio regression", ours, theirs)
     return stats
+
+
+def check_host_pipeline(library, ctx, n=2304, chunk=4096):
+    """Large, address-ordered host batches take the pipelined (sub-batched, 3-stream) path of
+    libdeflate_b200_*_batch_host; results must equal the plain path's."""
+    import ctypes
+    import numpy as np
+    import bench
+    synth = bench.load_synth()
+    buf = (ctypes.c_uint8 * (n * chunk))()
+    synth.synth_fill(buf, chunk, 0, n, 6, 4)
+    raw = bytes(buf)
+    inp = np.frombuffer(raw, dtype=np.uint8).copy()
+    bound = library.libdeflate_gzip_compress_bound(None, chunk)
+    comp = np.zeros(n * bound, dtype=np.uint8)
+    idx = np.arange(n, dtype=np.uint64)
+    ip = (inp.ctypes.data + idx * chunk).astype(np.uint64)
+    isz = np.full(n, chunk, dtype=np.uint64)
+    cp = (comp.ctypes.data + idx * bound).astype(np.uint64)
+    cav = np.full(n, bound, dtype=np.uint64)
+    csz = np.zeros(n, dtype=np.uint64)
+    rc = library.libdeflate_b200_compress_batch_host(ctx.h, 2, 6, ip.ctypes.data, isz.ctypes.data, cp.ctypes.data,
+                                                     cav.ctypes.data, csz.ctypes.data, n)
+    assert rc == 0 and (csz > 0).all()
+    for i in (0, 1, n // 2, n - 1):
+        assert zlib.decompress(comp[i * bound:i * bound + int(csz[i])].tobytes(), 31) == raw[i * chunk:(i + 1) * chunk]
+    out = np.zeros(n * chunk, dtype=np.uint8)
+    op = (out.ctypes.data + idx * chunk).astype(np.uint64)
+    oav = np.full(n, chunk, dtype=np.uint64)
+    aout = np.zeros(n, dtype=np.uint64)
+    res = np.zeros(n, dtype=np.int32)
+    rc = library.libdeflate_b200_decompress_batch_host(ctx.h, 2, 0, cp.ctypes.data, csz.ctypes.data, op.ctypes.data,
+                                                       oav.ctypes.data, None, aout.ctypes.data, res.ctypes.data, n)
+    assert rc == 0 and (res == 0).all() and (aout == chunk).all()
+    assert out.tobytes() == raw

@@ -44,3 +44,7 @@ def test_inflate_output_primitives_unit():
                            os.path.join(root, "tests", "emu", "copy_unit.cpp"), os.path.join(root, "tests", "emu", "cuda_emu.cpp"),
                            "-o", exe, "-lpthread"])
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_pipelined_host_path_emulated(emu, emu_ctx):
+    pc.check_host_pipeline(emu, emu_ctx)

@@ -116,6 +116,11 @@ def test_compress_batch_round_trip_and_bound(gpu_ctx, oracle):
                 assert r[0] == 0 and r[1] == c, (fmt, lvl, len(c))
 
 
+def test_pipelined_host_path(gpu_ctx):
+    import libdeflate_b200 as ldb
+    pc.check_host_pipeline(ldb.lib(), gpu_ctx, n=8192, chunk=65536)
+
+
 def test_full_size_property_round_trip(gpu_ctx):
     """BASELINE-sized chunks: 4096 x 64 KiB synthetic text, reference streams in,
     checksum-of-checksums out (size-independent property)."""
