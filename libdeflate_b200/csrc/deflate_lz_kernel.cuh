@@ -41,7 +41,7 @@
 #define LZ_NWIN      (LZ_PASS / 32)
 #define LZ_SEARCHERS (LZ_THREADS - 32)		// warp 0 inserts the next pass while the others search
 #ifndef LZ_RUN
-#define LZ_RUN       16			// consecutive positions per dynamically assigned search run
+#define LZ_RUN       32			// consecutive positions per dynamically assigned search run
 #endif
 #define LZ_SEG       16384			// largest single TMA load
 #define LZ_RING      65536
@@ -589,157 +589,68 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// chosen match covers (they inherit it at the same distance).  Every position
 				// still gets a (length, distance), so the exact parallel parse below can start a
 				// token anywhere.  One search call site per loop trip keeps the warp converged.
-				// The search is a per-lane state machine advanced in lock step by the warp: every
-				// trip each lane does ONE small piece of work (fetch a run, start a search, test
-				// one chain candidate, decide, or fill a few inherited positions).  Chains differ
-				// wildly in length (mean ~8, max 'depth'), so a nested "for position / for
-				// candidate" loop would leave most lanes idle behind the longest chain of each
-				// trip; the flat machine keeps them all walking their own chains.
 				const u32 min_len = v->min_len;
-				enum { S_FETCH, S_INIT, S_WALK, S_DECIDE, S_FILL, S_DONE };
-				u32 state = S_FETCH;
+				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
+				// (long matches, few searches) take more of them, which keeps the warp busy
 				u32 i = 0, i_end = 0;
 				u32 pL = 0, pD = 0;		// pending match at position i-1 (lazy evaluation in progress)
 				bool pending = false;
-				u32 p = 0, best_len = 0, best_dist = 0, max_len = 0, nice = 0, cur = 0, tailo = 0, tailv = 0;
-				u32 lim = 0, cand = 0, prev_dist = 0, dleft = 0;
-				u32 fk = 0, fstop = 0, mend = 0, fD = 0, next_i = 0;
 				for (;;) {
-					if (state == S_FETCH) {
-						// runs are handed out dynamically (shared counter): lanes whose runs are
-						// cheap take more of them
+					if (i >= i_end || b0 + i >= pend) {
 						const u32 r = atomicAdd(&v->run_counter, 1u);
 						i = r * LZ_RUN;
-						if (b0 + i >= pend || i >= LZ_PASS) {
-							state = S_DONE;
+						if (b0 + i >= pend || i >= LZ_PASS) break;
+						i_end = i + LZ_RUN;
+						pending = false;
+					}
+					const u32 p = b0 + i;
+					u32 L = 0, D = 0;
+					if (p + 4 <= n) {
+						if (pending) { L = pL - 1 >= 4 ? pL - 1 : 0; D = pD; }
+						lz_search(ring, nextt, p, n, pending ? (P.depth >> 1) : P.depth, (u32)P.nice, L, D);
+					}
+					rlen[i] = (u16)L;
+					roff[i] = (u16)(L ? D - 1 : 0);
+					u32 mpos, mL, mD;	// match to accept this trip (mL == 0: none)
+					if (pending) {
+						if (L >= pL && 4 * ((int)L - (int)pL) + ((int)(31 - __clz((int)pD)) - (int)(31 - __clz((int)D))) > 2) {
+							// the lookahead match is clearly better: literal at i-1, keep looking
+							// ahead from i unless it is long enough to take at once
+							mpos = i; mL = L >= (u32)P.nice ? L : 0; mD = D;
+							if (!mL) { pL = L; pD = D; }
+							pending = mL == 0;
 						} else {
-							i_end = i + LZ_RUN;
+							mpos = i - 1; mL = pL; mD = pD;
 							pending = false;
-							state = S_INIT;
 						}
-					}
-					if (state == S_INIT) {
-						if (i >= i_end || b0 + i >= pend) {
-							state = S_FETCH;
+					} else if (L >= min_len) {
+						if (P.lazy && L < (u32)P.nice && i + 1 < i_end && b0 + i + 1 < pend) {
+							pending = true; pL = L; pD = D;
+							mpos = i; mL = 0; mD = 0;
 						} else {
-							p = b0 + i;
-							if (p + 4 > n) {
-								rlen[i] = 0;
-								roff[i] = 0;
-								i++;
-								pending = false;
-							} else {
-								best_len = pending ? (pL - 1 >= 4 ? pL - 1 : 0) : 0;
-								best_dist = pD;
-								max_len = n - p < 258 ? n - p : 258;
-								nice = (u32)P.nice < max_len ? (u32)P.nice : max_len;
-								// a carried-over match may continue past where its predecessor was capped
-								if (best_len)
-									while (best_len < max_len && lz_ld8(ring, p + best_len) == lz_ld8(ring, p - best_dist + best_len)) best_len++;
-								if (best_len >= nice) {
-									state = S_DECIDE;
-								} else {
-									cur = lz_ld32(ring, p);
-									tailo = best_len >= 4 ? best_len - 3 : 0;
-									tailv = tailo ? lz_ld32(ring, p + tailo) : cur;
-									lim = p < LZ_MAX_DIST ? p : LZ_MAX_DIST;
-									cand = nextt[p & 0xffff];
-									prev_dist = 0;
-									dleft = pending ? (u32)(P.depth >> 1) : (u32)P.depth;
-									state = S_WALK;
-								}
-							}
+							mpos = i; mL = L; mD = D;
 						}
+					} else {
+						mpos = i; mL = 0; mD = 0;
 					}
-					if (state == S_WALK) {
-						// one chain candidate (ref: hc_matchfinder.h:268-332): newest first, within
-						// LZ_MAX_DIST, filtered by the byte just past the current best, then its last
-						// 4 bytes (hc_matchfinder.h:301-304), then the first 4
-						const u32 dist = (p - cand) & 0xffff;
-						if (dleft == 0 || dist - 1 >= lim || dist <= prev_dist) {
-							state = S_DECIDE;
-						} else {
-							dleft--;
-							prev_dist = dist;
-							const u32 cq = cand;	// positions are stored mod 65536 = ring index
-							cand = nextt[cq];
-							if (lz_ld8(ring, cq + tailo + 3) == (tailv >> 24) && lz_ld32(ring, cq + tailo) == tailv &&
-							    (!tailo || lz_ld32(ring, cq) == cur)) {
-								u32 len = 4;
-								while (len + 4 <= max_len) {
-									u32 x = lz_ld32(ring, p + len) ^ lz_ld32(ring, cq + len);
-									if (x) { len += (__ffs(x) - 1) >> 3; goto extended; }
-									len += 4;
-								}
-								while (len < max_len && lz_ld8(ring, p + len) == lz_ld8(ring, cq + len)) len++;
-							extended:
-								if (len > best_len) {
-									best_len = len;
-									best_dist = dist;
-									if (len >= nice) {
-										state = S_DECIDE;
-									} else {
-										tailo = len - 3;
-										tailv = lz_ld32(ring, p + tailo);
-									}
-								}
-							}
-						}
-					}
-					if (state == S_DECIDE) {
-						// the search at position i is complete (ref parser: deflate_compress.c:2605-2808)
-						const u32 L = best_len, D = best_dist;
-						rlen[i] = (u16)L;
-						roff[i] = (u16)(L ? D - 1 : 0);
-						u32 mpos = i, mL = 0, mD = 0;	// match accepted now (mL == 0: none)
-						if (pending) {
-							if (L >= pL && 4 * ((int)L - (int)pL) + ((int)(31 - __clz((int)pD)) - (int)(31 - __clz((int)D))) > 2) {
-								// the lookahead match is clearly better: literal at i-1; keep looking
-								// ahead from i unless it is long enough to take at once
-								if (L >= (u32)P.nice) { mpos = i; mL = L; mD = D; pending = false; }
-								else { pL = L; pD = D; }
-							} else {
-								mpos = i - 1; mL = pL; mD = pD;
-								pending = false;
-							}
-						} else if (L >= min_len) {
-							if (P.lazy && L < (u32)P.nice && i + 1 < i_end && b0 + i + 1 < pend) {
-								pending = true; pL = L; pD = D;
-							} else {
-								mpos = i; mL = L; mD = D;
-							}
-						}
-						if (mL) {
-							fstop = mpos + mL < i_end ? mpos + mL : i_end;
-							if (b0 + fstop > pend) fstop = pend - b0;
-							fk = i + 1;
-							mend = b0 + mpos + mL;
-							fD = mD;
-							next_i = mpos + mL;
-							state = S_FILL;
-						} else {
-							i++;
-							state = S_INIT;
-						}
-					}
-					if (state == S_FILL) {
+					if (mL) {
 						// positions covered by the accepted match inherit it at the same distance;
 						// 'mend' (end of the match at that distance) only moves forward, so extending
-						// inherited matches (needed when the match was capped at 258) is O(1) amortised
-#pragma unroll 1
-						for (int q = 0; q < 4 && fk < fstop; q++, fk++) {
-							const u32 pk = b0 + fk;
-							while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - fD)) mend++;
+						// the inherited matches (needed when the match was capped at 258) is O(1) amortised
+						u32 stop = mpos + mL < i_end ? mpos + mL : i_end;
+						if (b0 + stop > pend) stop = pend - b0;
+						u32 mend = b0 + mpos + mL;
+						for (u32 k = i + 1; k < stop; k++) {
+							const u32 pk = b0 + k;
+							while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - mD)) mend++;
 							u32 lk = mend - pk;
-							rlen[fk] = (u16)(lk >= 4 ? lk : 0);
-							roff[fk] = (u16)(lk >= 4 ? fD - 1 : 0);
+							rlen[k] = (u16)(lk >= 4 ? lk : 0);
+							roff[k] = (u16)(lk >= 4 ? mD - 1 : 0);
 						}
-						if (fk >= fstop) {
-							i = next_i;
-							state = S_INIT;
-						}
+						i = mpos + mL;
+					} else {
+						i++;
 					}
-					if (__all_sync(LDB_FULL_MASK, state == S_DONE)) break;
 				}
 			}
 			__syncthreads();
