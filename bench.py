@@ -498,6 +498,7 @@ def run_e2e(args, ctx, l, ldb, pin_in, n, chunk, fmt, cstride, barrier, allmax, 
 
 
 def main():
+    global LEVEL
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -506,9 +507,11 @@ def main():
     ap.add_argument("--workload", default="roundtrip", choices=["roundtrip", "decompress"])
     ap.add_argument("--chunks", type=int, default=NCHUNKS_DEFAULT)
     ap.add_argument("--chunk-size", type=int, default=CHUNK_DEFAULT)
+    ap.add_argument("--level", type=int, default=LEVEL, help="compression level (BASELINE configs[3] uses 12 with --chunk-size 1048576 --chunks 4096)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    LEVEL = args.level
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

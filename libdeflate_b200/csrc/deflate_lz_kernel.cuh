@@ -70,11 +70,17 @@
 #define LZ_SM_BYTES  (LZ_SM_VARS + 256)
 
 // per-CTA global scratch (L2 resident): per-position results of the current pass + tokens
-#define LZ_GS_RLEN   0						// u16[PASS]
-#define LZ_GS_ROFF   (LZ_GS_RLEN + 2 * LZ_PASS)			// u16[PASS]
-#define LZ_GS_EXIT   (LZ_GS_ROFF + 2 * LZ_PASS)			// u16[PASS]
+#define LZ_BLOCK_POS (LZ_BLOCK_PASSES * LZ_PASS)		// positions per block
+#define LZ_OPT_K     8					// matches kept per position (levels 10-12)
+#define LZ_DP_SEG    2048				// positions per independent DP segment (one warp each)
+#define LZ_GS_RLEN   0						// u16[BLOCK_POS]  block-relative
+#define LZ_GS_ROFF   (LZ_GS_RLEN + 2 * LZ_BLOCK_POS)		// u16[BLOCK_POS]
+#define LZ_GS_EXIT   (LZ_GS_ROFF + 2 * LZ_BLOCK_POS)		// u16[PASS]       pass-relative
 #define LZ_GS_TOK    (LZ_GS_EXIT + 2 * LZ_PASS)			// u32[TOKCAP]
-#define LZ_GS_BYTES  (LZ_GS_TOK + 4 * LZ_TOKCAP)
+#define LZ_GS_COST   (LZ_GS_TOK + 4 * LZ_TOKCAP)		// u32[BLOCK_POS + 320]   (levels 10-12)
+#define LZ_GS_MLIST  (LZ_GS_COST + 4 * (LZ_BLOCK_POS + 320))	// u32[BLOCK_POS * K]     (levels 10-12)
+#define LZ_GS_BYTES  (LZ_GS_MLIST + 4 * LZ_BLOCK_POS * LZ_OPT_K)
+#define LZ_COST_INF  0x3fffffu				// fits the 23-bit cost field of the DP reduction key
 
 struct lz_vars {
 	unsigned long long mbar;
@@ -97,6 +103,7 @@ struct lz_vars {
 
 struct lz_params {
 	int depth, nice, lazy;
+	int opt_iters;	// > 0: near-optimal parsing (levels 10-12): passes of min-cost-path + cost-model update
 };
 
 __device__ __forceinline__ lz_params lz_level_params(int level)
@@ -104,18 +111,19 @@ __device__ __forceinline__ lz_params lz_level_params(int level)
 	// level -> (max chain depth, nice length, lazy evaluation); cf. the reference's table
 	// lib/deflate_compress.c:3927-4013 (depth/nice per level; values here are ours)
 	switch (level) {
-	case 1: return {2, 16, 0};
-	case 2: return {4, 24, 0};
-	case 3: return {8, 32, 0};
-	case 4: return {12, 48, 0};
-	case 5: return {12, 48, 1};
-	case 6: return {24, 96, 1};
-	case 7: return {48, 160, 1};
-	case 8: return {96, 258, 1};
-	case 9: return {200, 258, 1};
-	case 10: return {300, 258, 1};
-	case 11: return {500, 258, 1};
-	default: return {800, 258, 1};
+	case 1: return {2, 16, 0, 0};
+	case 2: return {4, 24, 0, 0};
+	case 3: return {8, 32, 0, 0};
+	case 4: return {12, 48, 0, 0};
+	case 5: return {12, 48, 1, 0};
+	case 6: return {24, 96, 1, 0};
+	case 7: return {48, 160, 1, 0};
+	case 8: return {96, 258, 1, 0};
+	case 9: return {200, 258, 1, 0};
+	// near-optimal levels (ref: lib/deflate_compress.c:3972-4012: depth 35/100/300, passes 2/4/10)
+	case 10: return {48, 96, 1, 2};
+	case 11: return {96, 160, 1, 3};
+	default: return {200, 258, 1, 5};
 	}
 }
 
@@ -422,6 +430,144 @@ __device__ __forceinline__ void lz_search(const u8 *ring, const u16 *nextt, u32 
 	}
 }
 
+// ---- all-matches search for the near-optimal levels (stands in for bt_matchfinder_get_matches,
+// lib/bt_matchfinder.h:296: "matches of strictly increasing length", here read off the hash chain:
+// every improvement met while walking newest-to-oldest is a longer match at a larger distance,
+// i.e. the Pareto front the min-cost-path pass needs).  Up to LZ_OPT_K are kept (the first K-1 and
+// the longest).  Entry format: len << 16 | (dist - 1); 0 terminates.
+__device__ __forceinline__ void lz_search_all(const u8 *ring, const u16 *nextt, u32 p, u32 n, int depth, u32 nice_level,
+					       u32 *ml, u32 &best_len, u32 &best_dist)
+{
+	const u32 max_len = n - p < 258 ? n - p : 258;
+	const u32 nice = nice_level < max_len ? nice_level : max_len;
+	const u32 cur = lz_ld32(ring, p);
+	u32 tailo = 0, tailv = cur, cnt = 0;
+	best_len = 0;
+	best_dist = 0;
+	const u32 lim = p < LZ_MAX_DIST ? p : LZ_MAX_DIST;
+	u32 cand = nextt[p & 0xffff];
+	u32 prev_dist = 0;
+	for (int d = 0; d < depth; d++) {
+		const u32 dist = (p - cand) & 0xffff;
+		if (dist - 1 >= lim || dist <= prev_dist) break;
+		prev_dist = dist;
+		const u32 cq = cand;
+		cand = nextt[cq];
+		if (lz_ld8(ring, cq + tailo + 3) != (tailv >> 24)) continue;
+		if (lz_ld32(ring, cq + tailo) != tailv) continue;
+		if (tailo && lz_ld32(ring, cq) != cur) continue;
+		u32 len = 4;
+		while (len + 4 <= max_len) {
+			u32 x = lz_ld32(ring, p + len) ^ lz_ld32(ring, cq + len);
+			if (x) { len += (__ffs(x) - 1) >> 3; goto extended; }
+			len += 4;
+		}
+		while (len < max_len && lz_ld8(ring, p + len) == lz_ld8(ring, cq + len)) len++;
+	extended:
+		if (len > best_len) {
+			best_len = len;
+			best_dist = dist;
+			ml[cnt < LZ_OPT_K ? cnt : LZ_OPT_K - 1] = (len << 16) | (dist - 1);
+			cnt++;
+			if (len >= nice) break;
+			tailo = len - 3;
+			tailv = lz_ld32(ring, p + tailo);
+		}
+	}
+	for (u32 k = cnt; k < LZ_OPT_K; k++) ml[k] = 0;
+}
+
+// ---- min-cost path over one DP segment, executed by ONE warp (ref: deflate_find_min_cost_path,
+// lib/deflate_compress.c:3328-3399).  Block-relative positions [s0, s1), processed backwards:
+//   C[i] = min( lit_cost(byte_i) + C[i+1],  min over lengths L offered by the matches at i of
+//               len_cost(L) + off_cost(closest match of length >= L) + C[i+L] )
+// Lane k keeps C[i+1+k] in a register (the window slides by one shuffle per position), so the
+// 32 shortest candidate lengths need no memory at all; longer ones read the cost array.  A path
+// never crosses s1 (segments are independent; the price is one constrained token per 2048
+// positions).  The decision is written as a (length | flag, distance) pair the parallel parser
+// then follows: rlen = L (0 for a literal), roff = dist-1 | 0x8000.
+__device__ void lz_dp_segment(const u8 *ring, const u32 *mlist, u32 *costg, u16 *rlen, u16 *roff, const u8 *costtab,
+			      u32 block_begin, u32 s0, u32 s1, u32 lane)
+{
+	const u8 *litc = costtab, *lenc = costtab + 256, *offc = costtab + 256 + 259;
+	u32 wc = lane == 0 ? 0 : LZ_COST_INF;
+	u32 i = s1;
+	// tile of 4 positions x 8 match entries, one coalesced 128-byte load, fetched one tile ahead
+	auto load_tile = [&](u32 top) -> u32 {
+		// lane -> (q = lane >> 3: position top-1-q, j = lane & 7: entry)
+		u32 q = lane >> 3;
+		if (top < q + 1 || top - 1 - q < s0) return 0;
+		return mlist[(size_t)(top - 1 - q) * LZ_OPT_K + (lane & 7)];
+	};
+	u32 nxt = load_tile(i);
+	while (i > s0) {
+		const u32 curt = nxt;
+		nxt = i >= 4 ? load_tile(i - 4) : 0;
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			if (i < (u32)q + 1 || i - 1 - q < s0) break;
+			const u32 pos = i - 1 - q;
+			u32 m[LZ_OPT_K];
+#pragma unroll
+			for (int j = 0; j < LZ_OPT_K; j++) m[j] = __shfl_sync(LDB_FULL_MASK, curt, q * 8 + j);
+			u32 Lmax = 0;
+#pragma unroll
+			for (int j = 0; j < LZ_OPT_K; j++)
+				if (m[j]) Lmax = m[j] >> 16;
+			const u32 cap = s1 - pos;
+			if (Lmax > cap) Lmax = cap;
+			const u32 byte = ring[(block_begin + pos) & (LZ_RING - 1)];
+			// distance of the closest match offering length L (entries have increasing length)
+			auto dist_for = [&](u32 L) -> u32 {
+				u32 d = 0;
+#pragma unroll
+				for (int j = LZ_OPT_K - 1; j >= 0; j--)
+					if (m[j] && (m[j] >> 16) >= L) d = (m[j] & 0xffff) + 1;
+				return d;
+			};
+			u32 key;
+			{
+				const u32 L = lane + 1;
+				u32 cand = LZ_COST_INF;
+				if (lane == 0) cand = wc + litc[byte];
+				else if (L >= 4 && L <= Lmax) cand = wc + lenc[L] + offc[lz_off_slot(dist_for(L))];
+				if (cand > LZ_COST_INF) cand = LZ_COST_INF;
+				key = (cand << 9) | (L - 1);
+			}
+			for (u32 base = 32; base < Lmax; base += 32) {
+				const u32 L = base + lane + 1;
+				if (L <= Lmax) {
+					u32 c = pos + L == s1 ? 0 : costg[pos + L];
+					u32 cand = c + lenc[L] + offc[lz_off_slot(dist_for(L))];
+					if (cand > LZ_COST_INF) cand = LZ_COST_INF;
+					u32 k2 = (cand << 9) | (L - 1);
+					if (k2 < key) key = k2;
+				}
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				u32 other = __shfl_xor_sync(LDB_FULL_MASK, key, o);
+				if (other < key) key = other;
+			}
+			const u32 C = key >> 9, bestL = (key & 511) + 1;
+			if (lane == 0) {
+				costg[pos] = C;
+				if (bestL >= 3) {
+					rlen[pos] = (u16)bestL;
+					roff[pos] = (u16)((dist_for(bestL) - 1) | 0x8000);
+				} else {
+					rlen[pos] = 0;
+					roff[pos] = 0;
+				}
+			}
+			const u32 t = __shfl_up_sync(LDB_FULL_MASK, wc, 1);
+			wc = lane == 0 ? C : t;
+		}
+		i = i >= 4 ? i - 4 : 0;
+	}
+	__syncwarp();
+}
+
 // ---- the kernel ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 ldb_deflate_lz_kernel(ldb_deflate_args a)
@@ -453,6 +599,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 	u16 *roff = (u16 *)(gs + LZ_GS_ROFF);
 	u16 *exitt = (u16 *)(gs + LZ_GS_EXIT);
 	u32 *tokbuf = (u32 *)(gs + LZ_GS_TOK);
+	u32 *costg = (u32 *)(gs + LZ_GS_COST);
+	u32 *mlist = (u32 *)(gs + LZ_GS_MLIST);
+	u8 *costtab = sm + LZ_SM_ITEMS;	// lit[256] len[259] off[32] bit costs of the DP (the items region is free then)
 
 	const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const lz_params P = lz_level_params(a.level);
@@ -534,8 +683,183 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		o.obit = (u64)hdr_bytes * 8;
 		__syncthreads();
 
+		// ---- exact parallel parse of one pass (positions [pb0, ppend), results at rlen/roff[aoff + i]).
+		// forced: the DP already decided (flag set on matches); otherwise the lazy rule decides.
+		auto parse_pass = [&](const u32 pb0, const u32 ppend, const u32 aoff, const bool forced) {
+			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
+			const u32 nwin = (ppend - pb0 + 31) >> 5;
+			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
+				u32 i = w * 32 + lane;
+				u32 p = pb0 + i;
+				const u32 min_len = v->min_len;
+				u32 L0 = p < ppend ? rlen[aoff + i] : 0, O0 = p < ppend ? (roff[aoff + i] & 0x7fff) + 1 : 1;
+				bool is_match = forced ? ((L0 >= 3) && p < ppend) : (L0 >= min_len && p < ppend);
+				if (!forced && is_match && P.lazy && p + 1 < ppend) {
+					u32 L1 = rlen[aoff + i + 1], O1 = (roff[aoff + i + 1] & 0x7fff) + 1;
+					// ref: deflate_compress.c:2722-2725 -- prefer the next position's match if clearly better
+					if (L1 >= L0 && L0 < (u32)P.nice &&
+					    4 * ((int)L1 - (int)L0) + ((int)(31 - __clz((int)O0)) - (int)(31 - __clz((int)O1))) > 2)
+						is_match = false;
+				}
+				u32 step = is_match ? L0 : 1;
+				// decision flag in the top bit; the neighbour that reads roff[aoff + i] for its lazy test
+				// masks it off, and it only reads -- the flag is published after this warp's reads
+				__syncwarp();
+				if (is_match && !forced) roff[aoff + i] = (u16)((O0 - 1) | 0x8000);
+				u32 j = lane + step;
+#pragma unroll
+				for (int k = 0; k < 5; k++) {
+					u32 t = __shfl_sync(LDB_FULL_MASK, j, j & 31);
+					if (j < 32) j = t;
+				}
+				if (p < ppend) exitt[i] = (u16)j;
+			}
+			__syncthreads();
+			// (e2) chain the windows: warp 0 walks them in order; the 32 exits of a window sit in
+			// one register per lane (coalesced load, issued ahead of the deppendent chain) and the
+			// step is a shuffle
+			if (warp == 0) {
+				u32 e = v->parse_entry;
+				// double-buffered batches of 16 windows: the loads of batch k+1 are in flight
+				// while the deppendent shuffle chain of batch k runs
+				u32 exn[16];
+#pragma unroll
+				for (int k = 0; k < 16; k++) {
+					u32 i = (u32)k * 32 + lane;
+					exn[k] = ((u32)k < nwin && pb0 + i < ppend) ? exitt[i] : (lane + 1);
+				}
+				for (u32 w0 = 0; w0 < nwin; w0 += 16) {
+					u32 ex[16];
+#pragma unroll
+					for (int k = 0; k < 16; k++) ex[k] = exn[k];
+#pragma unroll
+					for (int k = 0; k < 16; k++) {
+						u32 w = w0 + 16 + k;
+						u32 i = w * 32 + lane;
+						exn[k] = (w < nwin && pb0 + i < ppend) ? exitt[i] : (lane + 1);
+					}
+#pragma unroll
+					for (int k = 0; k < 16; k++) {
+						u32 w = w0 + k;
+						if (w < nwin) {
+							u32 base = pb0 + w * 32;
+							bool inside = e >= base && e < base + 32 && e < ppend;
+							u32 x = __shfl_sync(LDB_FULL_MASK, ex[k], (e - base) & 31);
+							if (lane == 0) entryt[w] = inside ? (u8)(e - base) : 0xff;
+							if (inside) e = base + x;
+						}
+					}
+				}
+				if (e < ppend) e = ppend;
+				if (lane == 0) v->parse_entry = e;
+			}
+			__syncthreads();
+			// (e3) visited sets per window
+			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
+				u32 i = w * 32 + lane;
+				u32 e = entryt[w];
+				u32 V = 0;
+				if (e != 0xff) {
+					bool in_pass = pb0 + i < ppend;
+					u32 ro = in_pass ? roff[aoff + i] : 0;
+					u32 step = (ro & 0x8000) ? rlen[aoff + i] : 1;
+					u32 j = lane + step;
+					u32 jk[5];
+#pragma unroll
+					for (int k = 0; k < 5; k++) {
+						jk[k] = j;
+						u32 t = __shfl_sync(LDB_FULL_MASK, j, j & 31);
+						if (j < 32) j = t;
+					}
+					V = 1u << e;
+#pragma unroll
+					for (int k = 4; k >= 0; k--) {
+						u32 contrib = (((V >> lane) & 1) && jk[k] < 32) ? (1u << jk[k]) : 0;
+						V |= __reduce_or_sync(LDB_FULL_MASK, contrib);
+					}
+					// positions at or beyond the end of the pass are not tokens of this block
+					const u32 wbase = pb0 + w * 32;
+					if (wbase + 32 > ppend) V &= ppend > wbase ? ((1u << (ppend - wbase)) - 1) : 0;
+				}
+				if (lane == 0) vis[w] = V;
+			}
+			__syncthreads();
+			// (e4) token offsets (exclusive scan over windows) by warp 0
+			if (warp == 0) {
+				u32 run = 0;
+				for (u32 w0 = 0; w0 < nwin; w0 += 32) {
+					u32 w = w0 + lane;
+					u32 c = w < nwin ? (u32)__popc(vis[w]) : 0;
+					u32 incl = c;
+					for (int o2 = 1; o2 < 32; o2 <<= 1) {
+						u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
+						if (lane >= (u32)o2) incl += t;
+					}
+					if (w < nwin) tokoff[w] = run + incl - c;
+					run += __shfl_sync(LDB_FULL_MASK, incl, 31);
+				}
+				if (lane == 0) tokoff[LZ_NWIN] = run;
+			}
+			__syncthreads();
+			// (e5) emit tokens + histograms
+			const u32 tbase = v->tok_count;
+			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
+				u32 V = vis[w];
+				if (!V) continue;
+				u32 i = w * 32 + lane;
+				if ((V >> lane) & 1) {
+					u32 idx = tbase + tokoff[w] + __popc(V & ((1u << lane) - 1));
+					u32 ro = roff[aoff + i];
+					u32 len = rlen[aoff + i], off = (ro & 0x7fff) + 1;
+					// (a match that does not fit the data would be a bug upstream; never emit one)
+					if ((ro & 0x8000) && len >= 3 && len <= 258 && off <= pb0 + i && pb0 + i + len <= n) {
+						tokbuf[idx] = 0x80000000u | ((len - 3) << 15) | (off - 1);
+						atomicAdd(&freq[257 + lz_len_slot(len)], 1u);
+						atomicAdd(&freq[288 + lz_off_slot(off)], 1u);
+					} else {
+						u32 bv = lz_ld8(ring, pb0 + i);
+						tokbuf[idx] = bv;
+						atomicAdd(&freq[bv], 1u);
+					}
+				}
+			}
+			__syncthreads();
+			if (tid == 0) v->tok_count = tbase + tokoff[LZ_NWIN];
+			__syncthreads();
+		};
+
+		// ---- Huffman codes from freq[] -> lens[], codes[] (all threads)
+		auto build_codes = [&]() {
+			// (f1) Huffman codes.  Sorting by (freq, sym) is a parallel rank sort (one thread
+			// per symbol); the two-queue merges run on thread 0 (litlen) and thread 32 (offset).
+			if (tid == 0) { v->nused_lit = 0; v->nused_off = 0; }
+			__syncthreads();
+			if (tid < 320) {
+				const bool is_lit = tid < 288;
+				const u32 lo = is_lit ? 0 : 288, hi = is_lit ? 288 : 320;
+				const u32 f = freq[tid];
+				if (f) {
+					u32 rank = 0;
+					for (u32 t = lo; t < hi; t++) {
+						u32 ft = freq[t];
+						rank += (ft != 0) && (ft < f || (ft == f && t < tid));
+					}
+					(is_lit ? hsorted : osorted)[rank] = (u16)(tid - lo);
+					atomicAdd(is_lit ? &v->nused_lit : &v->nused_off, 1u);
+				}
+			}
+			__syncthreads();
+			if (tid == 0) lz_huffman_from_sorted(freq, hsorted, v->nused_lit, 288, 15, lens, hnodefreq, hparent);
+			if (tid == 32) lz_huffman_from_sorted(freq + 288, osorted, v->nused_off, 32, 15, lens + 288, onodefreq, oparent);
+			__syncthreads();
+			if (tid == 0) lz_gen_codes_serial(lens, 288, codes);
+			if (tid == 32) lz_gen_codes_serial(lens + 288, 32, codes + 288);
+			__syncthreads();
+		};
+
 		u32 loaded_end = 0;
 		u32 block_begin = 0;
+		u32 block_entry = 0;	// position of the first token of the current block
 		u32 pass_in_block = 0;
 
 		for (u32 b0 = 0; b0 < n; b0 += LZ_PASS) {
@@ -589,6 +913,22 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// chosen match covers (they inherit it at the same distance).  Every position
 				// still gets a (length, distance), so the exact parallel parse below can start a
 				// token anywhere.  One search call site per loop trip keeps the warp converged.
+				u16 *rl = rlen + pass_in_block * LZ_PASS, *rf = roff + pass_in_block * LZ_PASS;
+				if (P.opt_iters) {
+					// levels 10-12: every position is searched and keeps its list of matches
+					for (u32 i = tid - 32; b0 + i < pend; i += LZ_SEARCHERS) {
+						const u32 p = b0 + i;
+						u32 L = 0, D = 0;
+						u32 *ml = mlist + (size_t)(pass_in_block * LZ_PASS + i) * LZ_OPT_K;
+						if (p + 4 <= n) {
+							lz_search_all(ring, nextt, p, n, P.depth, (u32)P.nice, ml, L, D);
+						} else {
+							for (u32 k = 0; k < LZ_OPT_K; k++) ml[k] = 0;
+						}
+						rl[i] = (u16)L;
+						rf[i] = (u16)(L ? D - 1 : 0);
+					}
+				} else {
 				const u32 min_len = v->min_len;
 				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
 				// (long matches, few searches) take more of them, which keeps the warp busy
@@ -609,8 +949,8 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						if (pending) { L = pL - 1 >= 4 ? pL - 1 : 0; D = pD; }
 						lz_search(ring, nextt, p, n, pending ? (P.depth >> 1) : P.depth, (u32)P.nice, L, D);
 					}
-					rlen[i] = (u16)L;
-					roff[i] = (u16)(L ? D - 1 : 0);
+					rl[i] = (u16)L;
+					rf[i] = (u16)(L ? D - 1 : 0);
 					u32 mpos, mL, mD;	// match to accept this trip (mL == 0: none)
 					if (pending) {
 						if (L >= pL && 4 * ((int)L - (int)pL) + ((int)(31 - __clz((int)pD)) - (int)(31 - __clz((int)D))) > 2) {
@@ -644,191 +984,77 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 							const u32 pk = b0 + k;
 							while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - mD)) mend++;
 							u32 lk = mend - pk;
-							rlen[k] = (u16)(lk >= 4 ? lk : 0);
-							roff[k] = (u16)(lk >= 4 ? mD - 1 : 0);
+							rl[k] = (u16)(lk >= 4 ? lk : 0);
+							rf[k] = (u16)(lk >= 4 ? mD - 1 : 0);
 						}
 						i = mpos + mL;
 					} else {
 						i++;
 					}
 				}
+				}	// guided search (levels 1-9)
 			}
 			__syncthreads();
-			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
-			const u32 nwin = (pend - b0 + 31) >> 5;
-			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
-				u32 i = w * 32 + lane;
-				u32 p = b0 + i;
-				const u32 min_len = v->min_len;
-				u32 L0 = p < pend ? rlen[i] : 0, O0 = p < pend ? (roff[i] & 0x7fff) + 1 : 1;
-				bool is_match = L0 >= min_len && p < pend;
-				if (is_match && P.lazy && p + 1 < pend) {
-					u32 L1 = rlen[i + 1], O1 = (roff[i + 1] & 0x7fff) + 1;
-					// ref: deflate_compress.c:2722-2725 -- prefer the next position's match if clearly better
-					if (L1 >= L0 && L0 < (u32)P.nice &&
-					    4 * ((int)L1 - (int)L0) + ((int)(31 - __clz((int)O0)) - (int)(31 - __clz((int)O1))) > 2)
-						is_match = false;
-				}
-				u32 step = is_match ? L0 : 1;
-				// decision flag in the top bit; the neighbour that reads roff[i] for its lazy test
-				// masks it off, and it only reads -- the flag is published after this warp's reads
-				__syncwarp();
-				if (is_match) roff[i] = (u16)((O0 - 1) | 0x8000);
-				u32 j = lane + step;
-#pragma unroll
-				for (int k = 0; k < 5; k++) {
-					u32 t = __shfl_sync(LDB_FULL_MASK, j, j & 31);
-					if (j < 32) j = t;
-				}
-				if (p < pend) exitt[i] = (u16)j;
-			}
-			__syncthreads();
-			// (e2) chain the windows: warp 0 walks them in order; the 32 exits of a window sit in
-			// one register per lane (coalesced load, issued ahead of the dependent chain) and the
-			// step is a shuffle
-			if (warp == 0) {
-				u32 e = v->parse_entry;
-				// double-buffered batches of 16 windows: the loads of batch k+1 are in flight
-				// while the dependent shuffle chain of batch k runs
-				u32 exn[16];
-#pragma unroll
-				for (int k = 0; k < 16; k++) {
-					u32 i = (u32)k * 32 + lane;
-					exn[k] = ((u32)k < nwin && b0 + i < pend) ? exitt[i] : (lane + 1);
-				}
-				for (u32 w0 = 0; w0 < nwin; w0 += 16) {
-					u32 ex[16];
-#pragma unroll
-					for (int k = 0; k < 16; k++) ex[k] = exn[k];
-#pragma unroll
-					for (int k = 0; k < 16; k++) {
-						u32 w = w0 + 16 + k;
-						u32 i = w * 32 + lane;
-						exn[k] = (w < nwin && b0 + i < pend) ? exitt[i] : (lane + 1);
-					}
-#pragma unroll
-					for (int k = 0; k < 16; k++) {
-						u32 w = w0 + k;
-						if (w < nwin) {
-							u32 base = b0 + w * 32;
-							bool inside = e >= base && e < base + 32 && e < pend;
-							u32 x = __shfl_sync(LDB_FULL_MASK, ex[k], (e - base) & 31);
-							if (lane == 0) entryt[w] = inside ? (u8)(e - base) : 0xff;
-							if (inside) e = base + x;
-						}
-					}
-				}
-				if (e < pend) e = pend;
-				if (lane == 0) v->parse_entry = e;
-			}
-			__syncthreads();
-			// (e3) visited sets per window
-			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
-				u32 i = w * 32 + lane;
-				u32 e = entryt[w];
-				u32 V = 0;
-				if (e != 0xff) {
-					bool in_pass = b0 + i < pend;
-					u32 ro = in_pass ? roff[i] : 0;
-					u32 step = (ro & 0x8000) ? rlen[i] : 1;
-					u32 j = lane + step;
-					u32 jk[5];
-#pragma unroll
-					for (int k = 0; k < 5; k++) {
-						jk[k] = j;
-						u32 t = __shfl_sync(LDB_FULL_MASK, j, j & 31);
-						if (j < 32) j = t;
-					}
-					V = 1u << e;
-#pragma unroll
-					for (int k = 4; k >= 0; k--) {
-						u32 contrib = (((V >> lane) & 1) && jk[k] < 32) ? (1u << jk[k]) : 0;
-						V |= __reduce_or_sync(LDB_FULL_MASK, contrib);
-					}
-					// positions at or beyond the end of the pass are not tokens of this block
-					const u32 wbase = b0 + w * 32;
-					if (wbase + 32 > pend) V &= pend > wbase ? ((1u << (pend - wbase)) - 1) : 0;
-				}
-				if (lane == 0) vis[w] = V;
-			}
-			__syncthreads();
-			// (e4) token offsets (exclusive scan over windows) by warp 0
-			if (warp == 0) {
-				u32 run = 0;
-				for (u32 w0 = 0; w0 < nwin; w0 += 32) {
-					u32 w = w0 + lane;
-					u32 c = w < nwin ? (u32)__popc(vis[w]) : 0;
-					u32 incl = c;
-					for (int o2 = 1; o2 < 32; o2 <<= 1) {
-						u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
-						if (lane >= (u32)o2) incl += t;
-					}
-					if (w < nwin) tokoff[w] = run + incl - c;
-					run += __shfl_sync(LDB_FULL_MASK, incl, 31);
-				}
-				if (lane == 0) tokoff[LZ_NWIN] = run;
-			}
-			__syncthreads();
-			// (e5) emit tokens + histograms
-			const u32 tbase = v->tok_count;
-			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
-				u32 V = vis[w];
-				if (!V) continue;
-				u32 i = w * 32 + lane;
-				if ((V >> lane) & 1) {
-					u32 idx = tbase + tokoff[w] + __popc(V & ((1u << lane) - 1));
-					u32 ro = roff[i];
-					u32 len = rlen[i], off = (ro & 0x7fff) + 1;
-					// (a match that does not fit the data would be a bug upstream; never emit one)
-					if ((ro & 0x8000) && len >= 3 && len <= 258 && off <= b0 + i && b0 + i + len <= n) {
-						tokbuf[idx] = 0x80000000u | ((len - 3) << 15) | (off - 1);
-						atomicAdd(&freq[257 + lz_len_slot(len)], 1u);
-						atomicAdd(&freq[288 + lz_off_slot(off)], 1u);
-					} else {
-						u32 bv = lz_ld8(ring, b0 + i);
-						tokbuf[idx] = bv;
-						atomicAdd(&freq[bv], 1u);
-					}
-				}
-			}
-			__syncthreads();
-			if (tid == 0) v->tok_count = tbase + tokoff[LZ_NWIN];
-			__syncthreads();
+			// (e) exact parallel parse of this pass -> tokens + histograms
+			parse_pass(b0, pend, pass_in_block * LZ_PASS, false);
 			// ---- block boundary: every LZ_BLOCK_PASSES passes, or at the end of the input --------
 			pass_in_block++;
 			if (!(last || pass_in_block == LZ_BLOCK_PASSES)) continue;
+			const u32 npass_block = pass_in_block;
 			pass_in_block = 0;
 			const u32 block_end = pend;
+
+			// ---- levels 10-12: near-optimal parsing of the block (ref: deflate_optimize_and_flush_block,
+			// lib/deflate_compress.c:3417-3530).  Cost model = bit lengths of the Huffman codes of the
+			// previous parse; min-cost path by backward DP over independent 2048-position segments
+			// (one warp each); the resulting choices are re-parsed by the same parallel parser.
+			for (int it = 0; it < P.opt_iters; it++) {
+				if (tid == 0) freq[256] = 1;
+				__syncthreads();
+				build_codes();
+				// bit costs: unused symbols get a pessimistic default (cf. deflate_compress.c:149-151)
+				for (u32 k = tid; k < 256 + 259 + 32; k += LZ_THREADS) {
+					u32 c;
+					if (k < 256) {
+						c = lens[k] ? lens[k] : 13;
+					} else if (k < 256 + 259) {
+						u32 len = k - 256;
+						if (len < 3) c = 255;
+						else { u32 sl = lz_len_slot(len); c = (lens[257 + sl] ? lens[257 + sl] : 13) + lz_len_extra_bits(sl); }
+					} else {
+						u32 sl = k - 256 - 259;
+						c = (lens[288 + sl] ? lens[288 + sl] : 10) + lz_off_extra_bits(sl);
+					}
+					costtab[k] = (u8)c;
+				}
+				__syncthreads();
+				{
+					const u32 rel_entry = block_entry - block_begin;	// first token of the block
+					const u32 blen_pos = block_end - block_begin;
+					for (u32 seg = warp; seg * LZ_DP_SEG < blen_pos; seg += LZ_WARPS) {
+						u32 s0 = seg * LZ_DP_SEG, s1 = s0 + LZ_DP_SEG < blen_pos ? s0 + LZ_DP_SEG : blen_pos;
+						if (s0 < rel_entry) s0 = rel_entry;
+						if (s0 >= s1) continue;
+						lz_dp_segment(ring, mlist, costg, rlen, roff, costtab, block_begin, s0, s1, lane);
+					}
+				}
+				__syncthreads();
+				// re-parse the block with the chosen path
+				for (u32 k = tid; k < 320; k += LZ_THREADS) freq[k] = 0;
+				if (tid == 0) { v->tok_count = 0; v->parse_entry = block_entry; }
+				__syncthreads();
+				for (u32 pp = 0; pp < npass_block; pp++) {
+					u32 pb0 = block_begin + pp * LZ_PASS;
+					u32 ppend = pb0 + LZ_PASS < block_end ? pb0 + LZ_PASS : block_end;
+					parse_pass(pb0, ppend, pp * LZ_PASS, true);
+				}
+			}
 			const u32 ntok = v->tok_count;
 
 			// ======================= block flush =========================================
 			if (tid == 0) freq[256] = 1;
 			__syncthreads();
-			// (f1) Huffman codes.  Sorting by (freq, sym) is a parallel rank sort (one thread
-			// per symbol); the two-queue merges run on thread 0 (litlen) and thread 32 (offset).
-			if (tid == 0) { v->nused_lit = 0; v->nused_off = 0; }
-			__syncthreads();
-			if (tid < 320) {
-				const bool is_lit = tid < 288;
-				const u32 lo = is_lit ? 0 : 288, hi = is_lit ? 288 : 320;
-				const u32 f = freq[tid];
-				if (f) {
-					u32 rank = 0;
-					for (u32 t = lo; t < hi; t++) {
-						u32 ft = freq[t];
-						rank += (ft != 0) && (ft < f || (ft == f && t < tid));
-					}
-					(is_lit ? hsorted : osorted)[rank] = (u16)(tid - lo);
-					atomicAdd(is_lit ? &v->nused_lit : &v->nused_off, 1u);
-				}
-			}
-			__syncthreads();
-			if (tid == 0) lz_huffman_from_sorted(freq, hsorted, v->nused_lit, 288, 15, lens, hnodefreq, hparent);
-			if (tid == 32) lz_huffman_from_sorted(freq + 288, osorted, v->nused_off, 32, 15, lens + 288, onodefreq, oparent);
-			__syncthreads();
-			if (tid == 0) lz_gen_codes_serial(lens, 288, codes);
-			if (tid == 32) lz_gen_codes_serial(lens + 288, 32, codes + 288);
-			__syncthreads();
+			build_codes();
 			// (f2) precode items + precode (thread 0), ref: deflate_compress.c:1483-1631
 			if (tid == 0) {
 				u32 hlit = 288, hdist = 32;
@@ -1096,6 +1322,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			if (tid == 0) v->carry = stage[0];
 			// ---- next block ------------------------------------------------------------
 			block_begin = block_end;
+			block_entry = v->parse_entry;
 			for (u32 i = tid; i < 320; i += LZ_THREADS) freq[i] = 0;
 			if (tid == 0) v->tok_count = 0;
 			__syncthreads();
