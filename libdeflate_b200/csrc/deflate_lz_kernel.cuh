@@ -62,6 +62,8 @@
 #define LZ_SM_TOKOFF (LZ_SM_R + 4096)				//   parse: u32[NWIN + 16] token offsets
 #define LZ_SM_ENTRY  (LZ_SM_R + 8320)				//   parse: u8[NWIN] entry lane per window
 #define LZ_SM_ESCAN  (LZ_SM_R + 9344)				//   emission: scan scratch u32[80]
+#define LZ_SM_GEXIT  (LZ_SM_R + 9728)				//   parse: u16[WARPS * 32] group exits
+#define LZ_SM_GENTRY (LZ_SM_R + 10752)				//   parse: u32[WARPS] group entries
 #define LZ_SM_ITEMS  (LZ_SM_R + 12288)				// u16[512] precode items
 #define LZ_SM_FREQ   (LZ_SM_ITEMS + 1024)			// u32[288 + 32]
 #define LZ_SM_LENS   (LZ_SM_FREQ + 4 * 320)			// u8[320]
@@ -580,6 +582,8 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 	u32 *tokoff = (u32 *)(sm + LZ_SM_TOKOFF);
 	u8 *entryt = sm + LZ_SM_ENTRY;
 	u32 *escan = (u32 *)(sm + LZ_SM_ESCAN);
+	u16 *gexit = (u16 *)(sm + LZ_SM_GEXIT);
+	u32 *gentry = (u32 *)(sm + LZ_SM_GENTRY);
 	u32 *freq = (u32 *)(sm + LZ_SM_FREQ);
 	u8 *lens = sm + LZ_SM_LENS;
 	u16 *codes = (u16 *)(sm + LZ_SM_CODES);
@@ -688,14 +692,26 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		auto parse_pass = [&](const u32 pb0, const u32 ppend, const u32 aoff, const bool forced) {
 			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
 			const u32 nwin = (ppend - pb0 + 31) >> 5;
+			// (the loads of the next window are issued before the current one is processed)
+			const u32 min_len = v->min_len;
+			u32 nL0 = 0, nR0 = 0, nL1 = 0, nR1 = 0;
+			if (warp < nwin) {
+				u32 i = warp * 32 + lane;
+				if (pb0 + i < ppend) { nL0 = rlen[aoff + i]; nR0 = roff[aoff + i]; }
+				if (pb0 + i + 1 < ppend) { nL1 = rlen[aoff + i + 1]; nR1 = roff[aoff + i + 1]; }
+			}
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				u32 i = w * 32 + lane;
 				u32 p = pb0 + i;
-				const u32 min_len = v->min_len;
-				u32 L0 = p < ppend ? rlen[aoff + i] : 0, O0 = p < ppend ? (roff[aoff + i] & 0x7fff) + 1 : 1;
+				const u32 L0 = nL0, O0 = (nR0 & 0x7fff) + 1, L1 = nL1, O1 = (nR1 & 0x7fff) + 1;
+				if (w + LZ_WARPS < nwin) {
+					u32 i2 = i + LZ_WARPS * 32;
+					nL0 = 0; nR0 = 0; nL1 = 0; nR1 = 0;
+					if (pb0 + i2 < ppend) { nL0 = rlen[aoff + i2]; nR0 = roff[aoff + i2]; }
+					if (pb0 + i2 + 1 < ppend) { nL1 = rlen[aoff + i2 + 1]; nR1 = roff[aoff + i2 + 1]; }
+				}
 				bool is_match = forced ? ((L0 >= 3) && p < ppend) : (L0 >= min_len && p < ppend);
 				if (!forced && is_match && P.lazy && p + 1 < ppend) {
-					u32 L1 = rlen[aoff + i + 1], O1 = (roff[aoff + i + 1] & 0x7fff) + 1;
 					// ref: deflate_compress.c:2722-2725 -- prefer the next position's match if clearly better
 					if (L1 >= L0 && L0 < (u32)P.nice &&
 					    4 * ((int)L1 - (int)L0) + ((int)(31 - __clz((int)O0)) - (int)(31 - __clz((int)O1))) > 2)
@@ -715,43 +731,87 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				if (p < ppend) exitt[i] = (u16)j;
 			}
 			__syncthreads();
-			// (e2) chain the windows: warp 0 walks them in order; the 32 exits of a window sit in
-			// one register per lane (coalesced load, issued ahead of the deppendent chain) and the
-			// step is a shuffle
-			if (warp == 0) {
-				u32 e = v->parse_entry;
-				// double-buffered batches of 16 windows: the loads of batch k+1 are in flight
-				// while the deppendent shuffle chain of batch k runs
-				u32 exn[16];
+			// (e2) chain the windows.  A serial walk over all windows costs ~300 cycles per window on
+			// one warp, so it is split: (a) every warp composes the exits of ITS group of windows for
+			// all 32 possible entry lanes of the group's first window (per-lane shuffles), (b) warp 0
+			// chains the 16 groups, (c) every warp re-walks its group along the one real trajectory and
+			// records the entry lane of each window.
+			{
+				const u32 G = (nwin + LZ_WARPS - 1) / LZ_WARPS;		// windows per group
+				const u32 wg0 = warp * G;				// first window of my group
+				const u32 gstart = wg0 * 32;				// pass-relative position
+				// (a) exits of the group for entries gstart + lane
+				{
+					u32 pos = gstart + lane;
+					for (u32 k0 = 0; k0 < G; k0 += 8) {
+						u32 ex[8];
 #pragma unroll
-				for (int k = 0; k < 16; k++) {
-					u32 i = (u32)k * 32 + lane;
-					exn[k] = ((u32)k < nwin && pb0 + i < ppend) ? exitt[i] : (lane + 1);
-				}
-				for (u32 w0 = 0; w0 < nwin; w0 += 16) {
-					u32 ex[16];
+						for (int k = 0; k < 8; k++) {
+							u32 w = wg0 + k0 + k;
+							u32 i = w * 32 + lane;
+							ex[k] = (k0 + k < G && w < nwin && pb0 + i < ppend) ? exitt[i] : (lane + 1);
+						}
 #pragma unroll
-					for (int k = 0; k < 16; k++) ex[k] = exn[k];
-#pragma unroll
-					for (int k = 0; k < 16; k++) {
-						u32 w = w0 + 16 + k;
-						u32 i = w * 32 + lane;
-						exn[k] = (w < nwin && pb0 + i < ppend) ? exitt[i] : (lane + 1);
+						for (int k = 0; k < 8; k++) {
+							u32 w = wg0 + k0 + k;
+							u32 x = __shfl_sync(LDB_FULL_MASK, ex[k], pos & 31);
+							if (k0 + k < G && w < nwin && (pos >> 5) == w) pos = (w << 5) + x;
+						}
 					}
+					gexit[warp * 32 + lane] = (u16)(pos > 0xffff ? 0xffff : pos);
+				}
+				__syncthreads();
+				// (b) chain the groups (warp 0, all lanes redundantly; lane 0 publishes)
+				if (warp == 0) {
+					u32 e = v->parse_entry - pb0;	// pass-relative
+					for (u32 g = 0; g < LZ_WARPS; g++) {
+						const u32 gs = g * G * 32, ge = (g + 1) * G * 32;
+						u32 ent = 0xffffffffu;
+						if (e < ge && gs < (nwin << 5) && pb0 + e < ppend) {
+							ent = e;
+							if (e < gs + 32) {
+								e = gexit[g * 32 + (e - gs)];
+							} else {
+								// entered past the group's first window (a long match jumped in): walk it
+								for (u32 w = e >> 5; w < (g + 1) * G && w < nwin; w++) {
+									if ((e >> 5) == w) {
+										u32 i = w * 32 + (e & 31);
+										u32 x = pb0 + i < ppend ? exitt[i] : ((e & 31) + 1);
+										e = (w << 5) + x;
+									}
+								}
+							}
+						}
+						if (lane == 0) gentry[g] = ent;
+					}
+					u32 fin = pb0 + e;
+					if (fin < ppend) fin = ppend;
+					if (lane == 0) v->parse_entry = fin;
+				}
+				__syncthreads();
+				// (c) entry lane of every window of my group along the real trajectory
+				{
+					u32 pos = gentry[warp];
+					for (u32 k0 = 0; k0 < G; k0 += 8) {
+						u32 ex[8];
 #pragma unroll
-					for (int k = 0; k < 16; k++) {
-						u32 w = w0 + k;
-						if (w < nwin) {
-							u32 base = pb0 + w * 32;
-							bool inside = e >= base && e < base + 32 && e < ppend;
-							u32 x = __shfl_sync(LDB_FULL_MASK, ex[k], (e - base) & 31);
-							if (lane == 0) entryt[w] = inside ? (u8)(e - base) : 0xff;
-							if (inside) e = base + x;
+						for (int k = 0; k < 8; k++) {
+							u32 w = wg0 + k0 + k;
+							u32 i = w * 32 + lane;
+							ex[k] = (k0 + k < G && w < nwin && pb0 + i < ppend) ? exitt[i] : (lane + 1);
+						}
+#pragma unroll
+						for (int k = 0; k < 8; k++) {
+							u32 w = wg0 + k0 + k;
+							if (k0 + k < G && w < nwin) {
+								bool inside = pos != 0xffffffffu && (pos >> 5) == w && pb0 + pos < ppend;
+								u32 x = __shfl_sync(LDB_FULL_MASK, ex[k], pos & 31);
+								if (lane == 0) entryt[w] = inside ? (u8)(pos & 31) : 0xff;
+								if (inside) pos = (w << 5) + x;
+							}
 						}
 					}
 				}
-				if (e < ppend) e = ppend;
-				if (lane == 0) v->parse_entry = e;
 			}
 			__syncthreads();
 			// (e3) visited sets per window
