@@ -127,11 +127,32 @@ def load_cpub():
     return l
 
 
-def host_threads():
+def cpu_quota():
+    """CPUs this container may actually use: min(affinity mask, cgroup cpu.max quota)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            f = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if f[0] != "max":
+                    n = min(n, max(1, int(int(f[0]) / int(f[1]) + 0.5)))
+            else:
+                q = int(f[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
+def host_threads():
+    """Threads for the CPU reference arm: one per usable CPU (more only gets throttled by the quota)."""
+    return cpu_quota()
 
 
 def cpu_roundtrip(cpub, fmt, level, host_in, chunk, n, threads, want_streams=False):
@@ -187,7 +208,7 @@ def run_reference(args):
         "ms_per_step": round(1e3 * tsum / len(times), 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, n_override=n),
-        "cpu_baseline": {"value": round(value, 2), "unit": "MB/s", "cores": threads, "kind": "reference",
+        "cpu_baseline": {"value": round(value, 2), "unit": "MB/s", "cores": threads, "host_cpus_online": os.cpu_count(), "cpu_quota": cpu_quota(), "kind": "reference",
                          "sample": "%d x %d B chunks per step, gzip L%d compress+decompress with oracle/_ref (unmodified libdeflate), %d threads"
                                    % (n, chunk, LEVEL, threads) if args.workload == "roundtrip" else
                                    "%d x %d B chunks per step, raw DEFLATE decompress of reference L%d streams, %d threads" % (n, chunk, LEVEL, threads),
@@ -378,10 +399,10 @@ def run_b200(args):
     # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload ------------
     cpu_baseline = None
     if rank == 0 and world == 1 and cpub is not None and not args.no_cpu:
-        ns = min(n, max(1024, 512 * host_threads()))
+        ns = min(n, max(1024, 2048 * host_threads()))
         tc, td, total, _ = cpu_roundtrip(cpub, 2 if args.workload == "roundtrip" else 0, LEVEL, pin_in, chunk, ns, host_threads())
         t = (tc + td) if args.workload == "roundtrip" else td
-        cpu_baseline = {"value": round(ns * chunk / 1e6 / t, 2), "unit": "MB/s", "cores": host_threads(), "kind": "reference",
+        cpu_baseline = {"value": round(ns * chunk / 1e6 / t, 2), "unit": "MB/s", "cores": host_threads(), "host_cpus_online": os.cpu_count(), "cpu_quota": cpu_quota(), "kind": "reference",
                         "sample": "first %d chunks of the same batch, one pass, oracle/_ref (unmodified libdeflate 1.25, -O2) on %d host threads" % (ns, host_threads()),
                         "compress_MBps": round(ns * chunk / 1e6 / tc, 2), "decompress_MBps": round(ns * chunk / 1e6 / td, 2),
                         "ratio": round(total / float(ns * chunk), 4)}

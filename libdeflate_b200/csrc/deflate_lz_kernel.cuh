@@ -9,40 +9,46 @@
 // The output is a valid DEFLATE stream with a ratio close to the reference's at the
 // same level, never the reference's bytes (libdeflate.h:76-83 makes no such promise).
 //
-// B200 mapping: one persistent CTA (512 threads) per chunk; everything a chunk needs
-// lives in shared memory (~220 KiB):
+// B200 mapping: one persistent CTA (1024 threads) per chunk; everything a chunk needs
+// lives in shared memory (~224 KiB):
 //   * a 64 KiB ring of the input (the sliding window), filled 16 KiB at a time by the
 //     TMA bulk-copy engine (cp.async.bulk + mbarrier) -- the window never touches
 //     HBM again,
-//   * 15-bit hash heads (u16[32768]) and a chain table indexed by pos mod 32768
-//     (u16[32768]) holding positions mod 65536,
-//   * per batch of 4096 positions: chain insertion (one warp, ordered with
-//     __match_any_sync), then ALL 4096 positions searched in parallel (the
-//     reference searches only where its parser stands; searching everywhere is what
-//     makes the parser itself parallel), then a parallel lazy parse: per-window
-//     pointer jumping gives "where does a parse entering at lane e leave this
-//     32-position window" for all e at once, one thread chains the 128 windows,
-//     and __reduce_or_sync marks the visited positions,
-//   * tokens go to a per-CTA buffer in global memory (L2 resident), symbol
-//     histograms stay in shared memory,
-//   * per block: Huffman codes (length-limited to 15), exact bit cost of
-//     dynamic / static / stored (the reference's three-way choice, which is also
-//     what makes libdeflate_*_compress_bound() hold), then a two-pass emission:
-//     per-token bit lengths -> block-wide exclusive prefix sum -> every thread ORs
-//     its codewords into a shared-memory staging buffer -> coalesced stores.
+//   * 13-bit hash heads (u16[8192]) and a chain table with one slot per position
+//     mod 65536 (u16[65536]); a pass is 16 Ki positions and the window 32 Ki, so the
+//     16 Ki slots of the FOLLOWING pass are always dead and serve as scratch,
+//   * per pass of 16 Ki positions:
+//       - ordered chain insertion by the whole CTA: a stable multisplit of the positions
+//         by hash slice, then one warp per slice links its list (lz_insert_pass_par),
+//       - guided search: every thread walks dynamically assigned runs of 16 or 32
+//         positions like the reference's lazy parser, but every position ends up with a
+//         (length, distance), which is what lets the parse itself be parallel,
+//       - exact parallel lazy parse: per-window pointer jumping gives "where does a
+//         parse entering at lane e leave this 32-position window" for all e at once,
+//         the windows are chained group-parallel, __reduce_or_sync marks the visited
+//         positions, a prefix sum places the tokens,
+//   * tokens and per-position results go to a per-CTA buffer in global memory (L2
+//     resident), symbol histograms stay in shared memory,
+//   * per block (32 KiB of input): Huffman codes (length-limited to 15; parallel except
+//     for the two-queue merge), exact bit cost of dynamic / static / stored (the
+//     reference's three-way choice, which is also what makes
+//     libdeflate_*_compress_bound() hold), then a two-pass emission: per-token bit
+//     lengths -> block-wide exclusive prefix sum -> every thread ORs its codewords
+//     into a shared-memory staging buffer -> coalesced stores,
+//   * levels 10-12: all matches per position + iterated min-cost-path DP (see below).
 //
 // Algorithmic HBM bytes per chunk: in_nbytes (read once) + out_nbytes (written once).
 #pragma once
 
-#define LZ_THREADS   512
+#ifndef LZ_THREADS
+#define LZ_THREADS   1024
+#endif
 #define LZ_WARPS     (LZ_THREADS / 32)
 #define LZ_PASS      16384			// positions matched + parsed per pass
 #define LZ_BLOCK_PASSES 2			// passes per DEFLATE block (32 KiB of input)
 #define LZ_NWIN      (LZ_PASS / 32)
-#define LZ_SEARCHERS (LZ_THREADS - 32)		// warp 0 inserts the next pass while the others search
-#ifndef LZ_RUN
-#define LZ_RUN       32			// consecutive positions per dynamically assigned search run
-#endif
+#define LZ_NSL_BITS  (LZ_WARPS >= 32 ? 5 : 4)	// hash slices of the insertion = linking warps
+#define LZ_NSL       (1 << LZ_NSL_BITS)
 #define LZ_SEG       16384			// largest single TMA load
 #define LZ_RING      65536
 #define LZ_HASH_BITS 13
@@ -51,7 +57,8 @@
 #define LZ_MAX_DIST  (LZ_WIN - LZ_LOOKAHEAD)	// the oldest LOOKAHEAD bytes of the window are overwritten
 #define LZ_TOKCAP    (LZ_BLOCK_PASSES * LZ_PASS + 64)
 #define LZ_STAGE_WORDS 2048			// 8 KiB emission staging
-#define LZ_EMIT_ROUND  1024			// tokens per emission round (<= 48 bits each)
+#define LZ_TPT         (LZ_THREADS > 512 ? 1 : 2)	// tokens per thread per emission round
+#define LZ_EMIT_ROUND  (LZ_THREADS * LZ_TPT)	// tokens per emission round (<= 48 bits each, <= 1536 words)
 
 // shared memory layout
 #define LZ_SM_RING   0
@@ -63,7 +70,7 @@
 #define LZ_SM_ENTRY  (LZ_SM_R + 8320)				//   parse: u8[NWIN] entry lane per window
 #define LZ_SM_ESCAN  (LZ_SM_R + 9344)				//   emission: scan scratch u32[80]
 #define LZ_SM_GEXIT  (LZ_SM_R + 9728)				//   parse: u16[WARPS * 32] group exits
-#define LZ_SM_GENTRY (LZ_SM_R + 10752)				//   parse: u32[WARPS] group entries
+#define LZ_SM_GENTRY (LZ_SM_R + 11776)				//   parse: u32[WARPS] group entries (WARPS <= 32)
 #define LZ_SM_ITEMS  (LZ_SM_R + 12288)				// u16[512] precode items
 #define LZ_SM_FREQ   (LZ_SM_ITEMS + 1024)			// u32[288 + 32]
 #define LZ_SM_LENS   (LZ_SM_FREQ + 4 * 320)			// u8[320]
@@ -97,6 +104,7 @@ struct lz_vars {
 	u32 used_lits[8];	// 256-bit set of byte values seen in the first 4 KiB
 	u32 carry;		// partial output word at bit position obit (persists between flushes)
 	u32 nused_lit, nused_off;
+	u32 huff_over;		// a Huffman code exceeded 15 bits and was capped
 	u32 failed;
 	u32 obit_lo, obit_hi;	// output bit position (64-bit)
 	u32 pre_lens_packed[3];
@@ -329,6 +337,33 @@ __device__ void lz_build_huffman_small(const u32 *freq, u32 nsyms, u32 maxlen, u
 	lz_huffman_from_sorted(freq, sorted, nused, nsyms, maxlen, lens, nodefreq, parent);
 }
 
+// Two-queue Huffman merge only (one thread): leaves nodefreq[0, nused) ascending, internal nodes
+// appended behind them; writes parent[] for every node but the root.  The two queue heads and their
+// successors are kept in registers so that a shared-memory load is never waited for directly.
+__device__ __forceinline__ void lz_huffman_merge(u32 *nodefreq, u16 *parent, u32 nused)
+{
+	const u32 INF = 0xffffffffu;
+	u32 leaf = 0, inode = nused, nn = nused;
+	u32 l0 = nodefreq[0], l1 = nused > 1 ? nodefreq[1] : INF;	// leaf queue: head, next
+	u32 n0 = INF, n1 = INF;						// internal queue: head, next
+	while (nn < 2 * nused - 1) {
+		u32 a, b, fa, fb;
+		if (l0 <= n0) { a = leaf++; fa = l0; l0 = l1; l1 = leaf + 1 < nused ? nodefreq[leaf + 1] : INF; }
+		else { a = inode++; fa = n0; n0 = n1; n1 = INF; }
+		if (n0 == INF && inode < nn) n0 = nodefreq[inode];
+		if (l0 <= n0) { b = leaf++; fb = l0; l0 = l1; l1 = leaf + 1 < nused ? nodefreq[leaf + 1] : INF; }
+		else { b = inode++; fb = n0; n0 = n1; n1 = INF; }
+		const u32 sum = fa + fb;
+		nodefreq[nn] = sum;
+		parent[a] = (u16)nn;
+		parent[b] = (u16)nn;
+		nn++;
+		// refill the register copies of the internal queue (the new node may be its head)
+		if (n0 == INF && inode < nn) n0 = inode == nn - 1 ? sum : nodefreq[inode];
+		if (n1 == INF && inode + 1 < nn) n1 = inode + 1 == nn - 1 ? sum : nodefreq[inode + 1];
+	}
+}
+
 // canonical, bit-reversed codewords for an alphabet (all threads participate on disjoint syms)
 __device__ __forceinline__ void lz_gen_codes_serial(const u8 *lens, u32 nsyms, u16 *codes)
 {
@@ -348,40 +383,108 @@ __device__ __forceinline__ void lz_gen_codes_serial(const u8 *lens, u32 nsyms, u
 	}
 }
 
-// ---- ordered hash-chain insertion of one pass, executed by ONE warp --------------------------
-// For every position p: next[p] = most recent earlier position with the same 4-byte hash,
-// head[hash] = p (ref semantics: hc_matchfinder.h:227-232).  Same-hash lanes of a 32-position
-// tile are resolved with __match_any_sync; the tile's reads of head[] happen before its writes.
-// next[] has one slot per position mod 65536, so inserting a pass only reuses slots of
-// positions 64 KiB back -- outside every window -- and searches never see a clobbered link.
-__device__ __forceinline__ void lz_insert_pass(const u8 *ring, u16 *head, u16 *nextt, u32 b0, u32 pend, u32 n, u32 lane)
+#ifdef LZ_TIMING
+#include <stdio.h>
+// tuning builds only: cycles per phase, summed over all CTAs (thread 0's clock between barriers)
+__device__ unsigned long long ldb_lz_timing[16];
+#define LZ_T(k) do { if (tid == 0) { long long t_ = clock64(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
+#else
+#define LZ_T(k) do { } while (0)
+#endif
+
+// ---- ordered hash-chain insertion of one pass by the whole CTA -------------------------------
+// Chains must link every position to the previous one with the same hash, so insertion is ordered
+// -- but only within a hash value.  The head table is cut into LZ_NSL (16 or 32) slices by the top hash bits
+// and the pass is split stably by slice (a multisplit), after which one warp per slice links it:
+//  (1) warp w hashes its contiguous range of tiles, parks each hash in the position's own next[]
+//      slot (dead until the link is written) and counts its positions per slice;
+//  (2) a 2-D exclusive scan of the (warp, slice) counts gives every warp its write cursor in every
+//      slice list; the lists are packed into the 16 Ki next[] slots of the FOLLOWING pass, which
+//      belong to positions more than 48 Ki back -- outside every search window;
+//  (3) warp w re-walks its tiles in order and scatters the positions (rank inside a tile from
+//      __match_any_sync on the slice id): every list ends up sorted by position;
+//  (4) warp s links list s, 32 entries at a time: predecessors inside the batch come from
+//      __match_any_sync on the hash, the others from head[].  Same links as a serial insertion.
+__device__ __forceinline__ void lz_insert_pass_par(const u8 *ring, u16 *head, u16 *nextt, u32 *cmat,
+						   u32 b0, u32 pend, u32 n, u32 tid, u32 lane, u32 warp
+#ifdef LZ_TIMING
+						   , long long *tacc, long long &tlast
+#endif
+						   )
 {
+	static_assert(LZ_WARPS >= LZ_NSL && (LZ_WARPS * LZ_NSL + 2 * LZ_NSL) * 4 <= 8192, "one linking warp per slice");
+	u32 *sbase = cmat + LZ_WARPS * LZ_NSL, *stot = sbase + LZ_NSL;
 	const u32 lt = (1u << lane) - 1;
-	for (u32 base = b0; base < pend; base += 32) {
-		const u32 p = base + lane;
-		const bool valid = p < pend && p + 4 <= n;
-		const u32 h = valid ? lz_hash(lz_ld32(ring, p)) : 0;
-		const u32 old_head = valid ? head[h] : 0;
-		__syncwarp();
-		// optimistic step: everybody publishes itself as the new head; if every lane reads its
-		// own position back, all 32 hashes are distinct and the links are simply the old heads
-		if (valid) head[h] = (u16)p;
-		__syncwarp();
-		const bool lost = valid && head[h] != (u16)p;
-		if (!__any_sync(LDB_FULL_MASK, lost)) {
-			if (valid) nextt[p & 0xffff] = (u16)old_head;
-		} else {
-			// some lanes share a hash: order them (rare; __match_any_sync is slow)
-			const u32 m = __match_any_sync(LDB_FULL_MASK, valid ? h : (0x10000u | lane));
-			if (valid) {
-				const u32 below = m & lt;
-				const u32 pred = below ? (p - lane + (31 - __clz(below))) & 0xffff : old_head;
-				nextt[p & 0xffff] = (u16)pred;
-				if ((m >> lane) == 1) head[h] = (u16)p;	// highest lane of the group owns the head
+	const u32 LB = (b0 + LZ_PASS) & 0xffff;
+	const u32 ntiles = (pend - b0 + 31) >> 5, tpw = (ntiles + LZ_WARPS - 1) / LZ_WARPS;
+	const u32 r0 = b0 + warp * tpw * 32;
+	const u32 r1 = r0 + tpw * 32 < pend ? r0 + tpw * 32 : pend;
+	for (u32 i = tid; i < LZ_WARPS * LZ_NSL + 2 * LZ_NSL; i += LZ_THREADS) cmat[i] = 0;
+	__syncthreads();
+	for (u32 p = r0 + lane; p < r1; p += 32) {
+		const u32 hv = p + 4 <= n ? lz_hash(lz_ld32(ring, p)) : 0xffffu;
+		nextt[p & 0xffff] = (u16)hv;
+		if (hv != 0xffffu) atomicAdd(&cmat[warp * LZ_NSL + (hv >> (LZ_HASH_BITS - LZ_NSL_BITS))], 1u);
+	}
+	__syncthreads();
+	LZ_T(12);	// insertion: hashing
+	if (warp == 0) {
+		u32 run = 0;
+		if (lane < LZ_NSL)
+			for (u32 w = 0; w < LZ_WARPS; w++) {
+				const u32 c = cmat[w * LZ_NSL + lane];
+				cmat[w * LZ_NSL + lane] = run;
+				run += c;
 			}
+		u32 incl = run;
+		for (int o2 = 1; o2 < LZ_NSL; o2 <<= 1) {
+			const u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
+			if (lane >= (u32)o2) incl += t;
+		}
+		if (lane < LZ_NSL) { sbase[lane] = incl - run; stot[lane] = run; }
+	}
+	__syncthreads();
+	for (u32 t = 0; t < tpw; t++) {
+		const u32 p = r0 + 32 * t + lane;
+		const u32 hv = p < r1 ? nextt[p & 0xffff] : 0xffffu;
+		const bool valid = hv != 0xffffu;
+		const u32 sl = hv >> (LZ_HASH_BITS - LZ_NSL_BITS);
+		const u32 m = __match_any_sync(LDB_FULL_MASK, valid ? sl : (0x100u | lane));
+		const u32 cur = valid ? cmat[warp * LZ_NSL + sl] : 0;
+		__syncwarp();
+		if (valid) {
+			nextt[LB + sbase[sl] + cur + __popc(m & lt)] = (u16)p;
+			if ((m & lt) == 0) cmat[warp * LZ_NSL + sl] = cur + __popc(m);
 		}
 		__syncwarp();
 	}
+	__syncthreads();
+	LZ_T(13);	// insertion: slice lists
+	if (warp < LZ_NSL) {
+		const u32 cnt = stot[warp];
+		const u16 *mylist = nextt + LB + sbase[warp];
+		u32 p16n = lane < cnt ? mylist[lane] : 0;
+		u32 hn = lane < cnt ? nextt[p16n] : 0;
+		for (u32 b = 0; b < cnt; b += 32) {
+			const bool valid = b + lane < cnt;
+			const u32 p16 = p16n;
+			const u32 h = valid ? hn : (0x10000u | lane);
+			if (b + 32 + lane < cnt) {		// next batch: list entry and parked hash
+				p16n = mylist[b + 32 + lane];
+				hn = nextt[p16n];
+			}
+			const u32 old_head = valid ? head[h] : 0;
+			const u32 m = __match_any_sync(LDB_FULL_MASK, h);
+			const u32 below = m & lt;
+			const u32 prev = __shfl_sync(LDB_FULL_MASK, p16, below ? 31 - __clz(below) : 0);
+			if (valid) {
+				nextt[p16] = (u16)(below ? prev : old_head);
+				if ((m >> lane) == 1) head[h] = (u16)p16;	// newest position of its hash in this batch
+			}
+			__syncwarp();
+		}
+	}
+	__syncthreads();
 }
 
 // ---- one chain search (ref: hc_matchfinder.h:182-338) ------------------------------------------
@@ -608,6 +711,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 	u8 *costtab = sm + LZ_SM_ITEMS;	// lit[256] len[259] off[32] bit costs of the DP (the items region is free then)
 
 	const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef LZ_TIMING
+	long long tacc[16] = {};
+	long long tlast = clock64();
+#endif
 	const lz_params P = lz_level_params(a.level);
 
 	if (tid == 0) {
@@ -731,6 +838,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				if (p < ppend) exitt[i] = (u16)j;
 			}
 			__syncthreads();
+			LZ_T(8);
 			// (e2) chain the windows.  A serial walk over all windows costs ~300 cycles per window on
 			// one warp, so it is split: (a) every warp composes the exits of ITS group of windows for
 			// all 32 possible entry lanes of the group's first window (per-lane shuffles), (b) warp 0
@@ -814,15 +922,25 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				}
 			}
 			__syncthreads();
-			// (e3) visited sets per window
+			LZ_T(9);
+			// (e3) visited sets per window (the loads of the next window are issued first)
+			u32 e3_e = 0xff, e3_ro = 0, e3_rl = 0;
+			if (warp < nwin) {
+				const u32 i = warp * 32 + lane;
+				e3_e = entryt[warp];
+				if (e3_e != 0xff && pb0 + i < ppend) { e3_ro = roff[aoff + i]; e3_rl = rlen[aoff + i]; }
+			}
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
-				u32 i = w * 32 + lane;
-				u32 e = entryt[w];
+				const u32 e = e3_e, ro = e3_ro, rl = e3_rl;
+				if (w + LZ_WARPS < nwin) {
+					const u32 i2 = (w + LZ_WARPS) * 32 + lane;
+					e3_e = entryt[w + LZ_WARPS];
+					e3_ro = 0; e3_rl = 0;
+					if (e3_e != 0xff && pb0 + i2 < ppend) { e3_ro = roff[aoff + i2]; e3_rl = rlen[aoff + i2]; }
+				}
 				u32 V = 0;
 				if (e != 0xff) {
-					bool in_pass = pb0 + i < ppend;
-					u32 ro = in_pass ? roff[aoff + i] : 0;
-					u32 step = (ro & 0x8000) ? rlen[aoff + i] : 1;
+					u32 step = (ro & 0x8000) ? rl : 1;
 					u32 j = lane + step;
 					u32 jk[5];
 #pragma unroll
@@ -844,6 +962,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				if (lane == 0) vis[w] = V;
 			}
 			__syncthreads();
+			LZ_T(10);
 			// (e4) token offsets (exclusive scan over windows) by warp 0
 			if (warp == 0) {
 				u32 run = 0;
@@ -861,16 +980,28 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				if (lane == 0) tokoff[LZ_NWIN] = run;
 			}
 			__syncthreads();
+			LZ_T(11);
 			// (e5) emit tokens + histograms
 			const u32 tbase = v->tok_count;
+			u32 e5_V = 0, e5_ro = 0, e5_rl = 0;
+			if (warp < nwin) {
+				const u32 i = warp * 32 + lane;
+				e5_V = vis[warp];
+				if ((e5_V >> lane) & 1) { e5_ro = roff[aoff + i]; e5_rl = rlen[aoff + i]; }
+			}
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
-				u32 V = vis[w];
+				const u32 V = e5_V, ro = e5_ro;
+				const u32 len = e5_rl;
+				if (w + LZ_WARPS < nwin) {
+					const u32 i2 = (w + LZ_WARPS) * 32 + lane;
+					e5_V = vis[w + LZ_WARPS];
+					if ((e5_V >> lane) & 1) { e5_ro = roff[aoff + i2]; e5_rl = rlen[aoff + i2]; }
+				}
 				if (!V) continue;
 				u32 i = w * 32 + lane;
 				if ((V >> lane) & 1) {
 					u32 idx = tbase + tokoff[w] + __popc(V & ((1u << lane) - 1));
-					u32 ro = roff[aoff + i];
-					u32 len = rlen[aoff + i], off = (ro & 0x7fff) + 1;
+					u32 off = (ro & 0x7fff) + 1;
 					// (a match that does not fit the data would be a bug upstream; never emit one)
 					if ((ro & 0x8000) && len >= 3 && len <= 258 && off <= pb0 + i && pb0 + i + len <= n) {
 						tokbuf[idx] = 0x80000000u | ((len - 3) << 15) | (off - 1);
@@ -889,31 +1020,118 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		};
 
 		// ---- Huffman codes from freq[] -> lens[], codes[] (all threads)
-		auto build_codes = [&]() {
-			// (f1) Huffman codes.  Sorting by (freq, sym) is a parallel rank sort (one thread
-			// per symbol); the two-queue merges run on thread 0 (litlen) and thread 32 (offset).
-			if (tid == 0) { v->nused_lit = 0; v->nused_off = 0; }
+		// CTA-wide exclusive scan (all threads must call it); escan[0..64] is the scratch
+		auto cta_excl_scan = [&](u32 x, u32 &total) -> u32 {
+			u32 incl = x;
+			for (int o2 = 1; o2 < 32; o2 <<= 1) {
+				u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
+				if (lane >= (u32)o2) incl += t;
+			}
+			__syncthreads();		// earlier readers of escan are done
+			if (lane == 31) escan[warp] = incl;
 			__syncthreads();
+			if (warp == 0) {
+				u32 y = lane < LZ_WARPS ? escan[lane] : 0;
+				u32 yi = y;
+				for (int o2 = 1; o2 < 32; o2 <<= 1) {
+					u32 t = __shfl_up_sync(LDB_FULL_MASK, yi, o2);
+					if (lane >= (u32)o2) yi += t;
+				}
+				if (lane < LZ_WARPS) escan[32 + lane] = yi - y;
+				if (lane == LZ_WARPS - 1) escan[64] = yi;
+			}
+			__syncthreads();
+			total = escan[64];
+			return escan[32 + warp] + (incl - x);
+		};
+		auto build_codes = [&]() {
+			// (f1) Huffman codes for both alphabets.  Parallel: rank sort by (freq, sym), leaf depths
+			// (every leaf walks to the root), length assignment, canonical codewords (rank among the
+			// symbols of equal length).  Serial: only the two-queue merges, on thread 0 (litlen)
+			// and thread 32 (offset), and the rare Kraft repair after the 15-bit cap.
+			u32 *hcount = (u32 *)(sm + LZ_SM_GEXIT + 256), *ocount = hcount + 17;	// codewords per length
+			const bool is_lit = tid < 288;
+			const u32 lo = is_lit ? 0 : 288, hi = is_lit ? 288 : 320;
+			if (tid == 0) { v->nused_lit = 0; v->nused_off = 0; v->huff_over = 0; }
+			if (tid < 34) hcount[tid] = 0;
+			__syncthreads();
+			u32 myrank = 0xffffffffu;
 			if (tid < 320) {
-				const bool is_lit = tid < 288;
-				const u32 lo = is_lit ? 0 : 288, hi = is_lit ? 288 : 320;
 				const u32 f = freq[tid];
+				lens[tid] = 0;
 				if (f) {
 					u32 rank = 0;
 					for (u32 t = lo; t < hi; t++) {
 						u32 ft = freq[t];
 						rank += (ft != 0) && (ft < f || (ft == f && t < tid));
 					}
+					myrank = rank;
 					(is_lit ? hsorted : osorted)[rank] = (u16)(tid - lo);
+					(is_lit ? hnodefreq : onodefreq)[rank] = f;
 					atomicAdd(is_lit ? &v->nused_lit : &v->nused_off, 1u);
 				}
 			}
 			__syncthreads();
-			if (tid == 0) lz_huffman_from_sorted(freq, hsorted, v->nused_lit, 288, 15, lens, hnodefreq, hparent);
-			if (tid == 32) lz_huffman_from_sorted(freq + 288, osorted, v->nused_off, 32, 15, lens + 288, onodefreq, oparent);
+			const u32 nused = is_lit ? v->nused_lit : v->nused_off;
+			if (tid == 0 && nused >= 2) lz_huffman_merge(hnodefreq, hparent, nused);
+			if (tid == 32) { const u32 nu = v->nused_off; if (nu >= 2) lz_huffman_merge(onodefreq, oparent, nu); }
 			__syncthreads();
-			if (tid == 0) lz_gen_codes_serial(lens, 288, codes);
-			if (tid == 32) lz_gen_codes_serial(lens + 288, 32, codes + 288);
+			if (tid < 320 && myrank != 0xffffffffu && nused >= 2) {
+				const u16 *par = is_lit ? hparent : oparent;
+				const u32 root = 2 * nused - 2;
+				u32 node = myrank, d = 0;
+				while (node != root && d <= 15) { node = par[node]; d++; }
+				if (d > 15) { d = 15; v->huff_over = 1; }
+				atomicAdd(&(is_lit ? hcount : ocount)[d], 1u);
+			}
+			__syncthreads();
+			if ((tid == 0 || tid == 288) && nused < 2) {
+				// at least two codewords (ref: deflate_compress.c:1369-1378)
+				u8 *ln = lens + lo;
+				u32 *cn = is_lit ? hcount : ocount;
+				if (nused == 0) { ln[0] = 1; ln[1] = 1; }
+				else { const u32 sy = (is_lit ? hsorted : osorted)[0]; ln[sy] = 1; ln[sy ? 0 : 1] = 1; }
+				cn[1] = 2;
+			}
+			if ((tid == 0 || tid == 32) && v->huff_over) {
+				// restore the Kraft sum to exactly 1 by lengthening the cheapest leaves
+				u32 *cn = tid == 0 ? hcount : ocount;
+				u32 kraft = 0;
+				for (u32 l = 1; l <= 15; l++) kraft += cn[l] << (15 - l);
+				while (kraft > (1u << 15)) {
+					u32 l = 14;
+					while (cn[l] == 0) l--;
+					cn[l]--;
+					cn[l + 1] += 2;
+					cn[15]--;
+					kraft -= 1;
+				}
+			}
+			__syncthreads();
+			if (tid < 320 && myrank != 0xffffffffu && nused >= 2) {
+				// rarest symbols get the longest codes
+				const u32 *cn = is_lit ? hcount : ocount;
+				u32 cum = 0, len = 1;
+				for (u32 l = 15; l >= 1; l--) {
+					cum += cn[l];
+					if (myrank < cum) { len = l; break; }
+				}
+				lens[tid] = (u8)len;
+			}
+			__syncthreads();
+			if (tid < 320) {
+				const u32 l = lens[tid];
+				u32 code = 0;
+				if (l) {
+					const u32 *cn = is_lit ? hcount : ocount;
+					u32 first = 0;
+					for (u32 k = 1; k < l; k++) first = (first + cn[k]) << 1;
+					u32 same = 0;
+					for (u32 t = lo; t < tid; t++) same += lens[t] == l;
+					code = __brev(first + same) >> (32 - l);
+				}
+				codes[tid] = (u16)code;
+			}
 			__syncthreads();
 		};
 
@@ -957,16 +1175,17 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					for (int k = 0; k < 8; k++) cnt += __popc(v->used_lits[k]);
 					v->min_len = n < 512 ? 4 : lz_choose_min_len(cnt, (u32)P.depth);
 				}
-				if (warp == 0) lz_insert_pass(ring, head, nextt, 0, pend, n, lane);
 				__syncthreads();
 			}
-			// (b) warp 0 inserts the NEXT pass into the hash chains (ordered) while the other 15
-			// warps search THIS pass.  next[] has a slot per position mod 65536 and a pass is
-			// 16 Ki positions, so the slots written now belong to positions 48..64 Ki back --
-			// outside every window -- and the searchers only follow links of older positions.
-			if (warp == 0) {
-				if (!last) lz_insert_pass(ring, head, nextt, pend, pend + LZ_PASS < n ? pend + LZ_PASS : n, n, lane);
-			} else {
+			// (b) the whole CTA links this pass into the hash chains (ordered within a hash)
+			LZ_T(0);	// loads + first-pass extras
+#ifdef LZ_TIMING
+			lz_insert_pass_par(ring, head, nextt, (u32 *)(sm + LZ_SM_R), b0, pend, n, tid, lane, warp, tacc, tlast);
+#else
+			lz_insert_pass_par(ring, head, nextt, (u32 *)(sm + LZ_SM_R), b0, pend, n, tid, lane, warp);
+#endif
+			LZ_T(3);	// insertion: linking
+			{
 				// (c) guided search.  Every searcher owns a run of consecutive positions and walks
 				// it like the reference's lazy parser (deflate_compress.c:2605-2808): search where
 				// a token could start, look one position ahead, then skip the positions the
@@ -976,7 +1195,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				u16 *rl = rlen + pass_in_block * LZ_PASS, *rf = roff + pass_in_block * LZ_PASS;
 				if (P.opt_iters) {
 					// levels 10-12: every position is searched and keeps its list of matches
-					for (u32 i = tid - 32; b0 + i < pend; i += LZ_SEARCHERS) {
+					for (u32 i = tid; b0 + i < pend; i += LZ_THREADS) {
 						const u32 p = b0 + i;
 						u32 L = 0, D = 0;
 						u32 *ml = mlist + (size_t)(pass_in_block * LZ_PASS + i) * LZ_OPT_K;
@@ -990,6 +1209,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					}
 				} else {
 				const u32 min_len = v->min_len;
+				// A run starts its walk without knowing where the parse really enters it, so short
+				// runs cost a little ratio (L6: +0.9 % at 16 vs 32) and buy parallelism; the deep
+				// levels, which are chosen for ratio, keep 32.
+				const u32 run_len = a.level >= 7 ? 32 : 16;
 				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
 				// (long matches, few searches) take more of them, which keeps the warp busy
 				u32 i = 0, i_end = 0;
@@ -998,9 +1221,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				for (;;) {
 					if (i >= i_end || b0 + i >= pend) {
 						const u32 r = atomicAdd(&v->run_counter, 1u);
-						i = r * LZ_RUN;
+						i = r * run_len;
 						if (b0 + i >= pend || i >= LZ_PASS) break;
-						i_end = i + LZ_RUN;
+						i_end = i + run_len;
 						pending = false;
 					}
 					const u32 p = b0 + i;
@@ -1055,8 +1278,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				}	// guided search (levels 1-9)
 			}
 			__syncthreads();
+			LZ_T(1);	// search phase (barrier to barrier)
 			// (e) exact parallel parse of this pass -> tokens + histograms
 			parse_pass(b0, pend, pass_in_block * LZ_PASS, false);
+			LZ_T(2);	// parse
 			// ---- block boundary: every LZ_BLOCK_PASSES passes, or at the end of the input --------
 			pass_in_block++;
 			if (!(last || pass_in_block == LZ_BLOCK_PASSES)) continue;
@@ -1112,52 +1337,96 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			const u32 ntok = v->tok_count;
 
 			// ======================= block flush =========================================
+			LZ_T(7);	// optimal-parse iterations
 			if (tid == 0) freq[256] = 1;
 			__syncthreads();
 			build_codes();
-			// (f2) precode items + precode (thread 0), ref: deflate_compress.c:1483-1631
+			LZ_T(4);	// Huffman codes
+			// (f2) precode items + precode, ref: deflate_compress.c:1483-1631.  Run-length items in
+			// parallel: thread j looks at code length j of the hlit+hdist sequence, run starts are
+			// found with ballots, every start knows in closed form how many items its run becomes,
+			// a CTA scan places them.  Only the 19-symbol precode itself is built by one thread.
+			u32 *pfreq_sm = (u32 *)(sm + LZ_SM_GEXIT);		// u32[19] (region unused while flushing)
+			u8 *plens_sm = sm + LZ_SM_GEXIT + 128;			// u8[19]
+			u16 *pcodes_sm = (u16 *)(sm + LZ_SM_GEXIT + 160);	// u16[19]
 			if (tid == 0) {
-				u32 hlit = 288, hdist = 32;
+				u32 hlit = 288;
 				while (hlit > 257 && lens[hlit - 1] == 0) hlit--;
+				v->hlit = hlit;
+			}
+			if (tid == 32) {
+				u32 hdist = 32;
 				while (hdist > 1 && lens[288 + hdist - 1] == 0) hdist--;
-				u32 pfreq[19];
-				for (int k = 0; k < 19; k++) pfreq[k] = 0;
-				u32 ni = 0, total = hlit + hdist, i = 0;
-				while (i < total) {
-					u32 val = i < hlit ? lens[i] : lens[288 + i - hlit];
-					u32 run = 1;
-					while (i + run < total) {
-						u32 nv = (i + run) < hlit ? lens[i + run] : lens[288 + i + run - hlit];
-						if (nv != val) break;
-						run++;
+				v->hdist = hdist;
+			}
+			if (tid >= 64 && tid < 64 + 19) pfreq_sm[tid - 64] = 0;
+			__syncthreads();
+			{
+				const u32 hlit = v->hlit, total = hlit + v->hdist;
+				const u32 j = tid;
+				const bool inb = j < total;
+				const u32 val = inb ? (j < hlit ? lens[j] : lens[288 + j - hlit]) : 0xff;
+				const u32 prv = (inb && j > 0) ? (j - 1 < hlit ? lens[j - 1] : lens[288 + j - 1 - hlit]) : 0xfe;
+				const bool isstart = inb && val != prv;
+				const u32 smask = __ballot_sync(LDB_FULL_MASK, isstart);
+				if (lane == 0 && warp < 10) escan[66 + warp] = smask;
+				__syncthreads();
+				u32 run = 0, cnt = 0;
+				if (isstart) {
+					u32 nxt = total;
+					u32 m = lane == 31 ? 0 : (smask & ~((2u << lane) - 1));
+					if (m) nxt = warp * 32 + __ffs(m) - 1;
+					else {
+						for (u32 w = warp + 1; w < 10; w++) {
+							u32 mm = escan[66 + w];
+							if (mm) { nxt = w * 32 + __ffs(mm) - 1; break; }
+						}
 					}
+					run = nxt - j;
+					if (val == 0) {
+						u32 rem = run % 138;
+						cnt = run / 138 + (rem >= 3 ? 1 : rem);
+					} else if (run >= 4) {
+						u32 rem = (run - 1) % 6;
+						cnt = 1 + (run - 1) / 6 + (rem >= 3 ? 1 : rem);
+					} else cnt = run;
+				}
+				u32 ntot;
+				const u32 off = cta_excl_scan(cnt, ntot);
+				if (isstart) {
+					u32 ni = off;
 					if (val == 0) {
 						while (run >= 11) {
 							u32 r = run < 138 ? run : 138;
 							items[ni++] = (u16)(18 | ((r - 11) << 5));
-							pfreq[18]++;
-							run -= r; i += r;
+							atomicAdd(&pfreq_sm[18], 1u);
+							run -= r;
 						}
 						if (run >= 3) {
 							items[ni++] = (u16)(17 | ((run - 3) << 5));
-							pfreq[17]++;
-							i += run; run = 0;
+							atomicAdd(&pfreq_sm[17], 1u);
+							run = 0;
 						}
 					} else if (run >= 4) {
-						items[ni++] = (u16)val; pfreq[val]++;
-						run--; i++;
+						items[ni++] = (u16)val;
+						atomicAdd(&pfreq_sm[val], 1u);
+						run--;
 						while (run >= 3) {
 							u32 r = run < 6 ? run : 6;
 							items[ni++] = (u16)(16 | ((r - 3) << 5));
-							pfreq[16]++;
-							run -= r; i += r;
+							atomicAdd(&pfreq_sm[16], 1u);
+							run -= r;
 						}
 					}
-					while (run) {
-						items[ni++] = (u16)val; pfreq[val]++;
-						run--; i++;
-					}
+					if (run) atomicAdd(&pfreq_sm[val], run);
+					while (run) { items[ni++] = (u16)val; run--; }
 				}
+				if (tid == 0) v->n_items = ntot;
+			}
+			__syncthreads();
+			if (tid == 0) {
+				u32 pfreq[19];
+				for (int k = 0; k < 19; k++) pfreq[k] = pfreq_sm[k];
 				u8 plens[19];
 				u16 psorted[19];
 				u32 pnodef[38];
@@ -1170,15 +1439,15 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				for (int k = 0; k < 19; k++) cost += pfreq[k] * plens[k];
 				cost += 2 * pfreq[16] + 3 * pfreq[17] + 7 * pfreq[18];
 				v->cost_dyn = cost;
-				v->hlit = hlit; v->hdist = hdist; v->hclen = hclen; v->n_items = ni;
-				u64 pk = 0;
-				for (int k = 0; k < 19; k++) pk |= (u64)plens[k] << (3 * k);
-				v->pre_lens_packed[0] = (u32)pk;
-				v->pre_lens_packed[1] = (u32)(pk >> 32);
+				v->hclen = hclen;
+				u16 pcodes[19];
+				lz_gen_codes_serial(plens, 19, pcodes);
+				for (int k = 0; k < 19; k++) { plens_sm[k] = plens[k]; pcodes_sm[k] = pcodes[k]; }
 				v->cost_static = 3;
 				v->extra_bits = 0;
 			}
 			__syncthreads();
+			LZ_T(5);	// precode
 			// (f3) symbol costs (ref: deflate_compress.c:1750-1808)
 			if (tid < 320) {
 				u32 f = freq[tid];
@@ -1270,45 +1539,47 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					if (tid == 32) lz_gen_codes_serial(lens + 288, 32, codes + 288);
 					__syncthreads();
 				}
-				// header, serial (thread 0), directly into staging
-				if (tid == 0) {
-					u32 rb = (u32)(o.obit - (w0 << 5));
-					lz_stage_or(stage, rb, (last ? 1 : 0) | (btype << 1), 3);
-					rb += 3;
+				// header: fixed fields by thread 0, the precode items by one thread each (bit offsets
+				// from a CTA scan), directly into staging
+				u32 rel;
+				{
+					const u32 rb0 = (u32)(o.obit - (w0 << 5));
+					u32 rb = rb0 + 3;
+					if (tid == 0) lz_stage_or(stage, rb0, (last ? 1 : 0) | (btype << 1), 3);
 					if (btype == DEFLATE_BLOCKTYPE_DYNAMIC) {
-						const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-						u64 pk = (u64)v->pre_lens_packed[0] | ((u64)v->pre_lens_packed[1] << 32);
-						u8 plens[19];
-						u16 pcodes[19];
-						for (int k = 0; k < 19; k++) plens[k] = (u8)((pk >> (3 * k)) & 7);
-						lz_gen_codes_serial(plens, 19, pcodes);
-						lz_stage_or(stage, rb, (v->hlit - 257) | ((v->hdist - 1) << 5) | ((v->hclen - 4) << 10), 14);
+						const u32 hclen = v->hclen, nit = v->n_items;
+						if (tid == 0)
+							lz_stage_or(stage, rb, (v->hlit - 257) | ((v->hdist - 1) << 5) | ((hclen - 4) << 10), 14);
 						rb += 14;
-						for (u32 k = 0; k < v->hclen; k++) {
-							lz_stage_or(stage, rb, plens[perm[k]], 3);
-							rb += 3;
+						if (tid < hclen) {
+							const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+							lz_stage_or(stage, rb + 3 * tid, plens_sm[perm[tid]], 3);
 						}
-						for (u32 k = 0; k < v->n_items; k++) {
-							u32 it = items[k], sym = it & 31, ex = it >> 5;
-							lz_stage_or(stage, rb, pcodes[sym], plens[sym]);
-							rb += plens[sym];
-							u32 eb = sym == 16 ? 2 : (sym == 17 ? 3 : (sym == 18 ? 7 : 0));
-							lz_stage_or(stage, rb, ex, eb);
-							rb += eb;
+						rb += 3 * hclen;
+						u32 nb = 0, bits = 0;
+						if (tid < nit) {
+							const u32 it = items[tid], sym = it & 31, ex = it >> 5;
+							const u32 pl = plens_sm[sym];
+							const u32 eb = sym == 16 ? 2 : (sym == 17 ? 3 : (sym == 18 ? 7 : 0));
+							bits = pcodes_sm[sym] | (ex << pl);
+							nb = pl + eb;
 						}
+						u32 hbits;
+						const u32 hoff = cta_excl_scan(nb, hbits);
+						lz_stage_or(stage, rb + hoff, bits, nb);
+						rb += hbits;
 					}
-					v->obit_lo = rb;	// relative bit position after the header
+					rel = rb;	// bits used in staging so far (relative to word w0)
 				}
 				__syncthreads();
-				u32 rel = v->obit_lo;	// bits used in staging so far (relative to word w0)
 				// token rounds: bit lengths -> exclusive scan -> OR into staging -> flush whole words
 				for (u32 t0 = 0; t0 <= ntok; t0 += LZ_EMIT_ROUND) {
 					// (the EOB symbol is token index ntok)
-					u32 mybits[2] = {0, 0};
-					u64 myval[2] = {0, 0};
+					u32 mybits[LZ_TPT] = {};
+					u64 myval[LZ_TPT] = {};
 #pragma unroll
-					for (int r = 0; r < 2; r++) {
-						u32 ti = t0 + tid * 2 + r;
+					for (int r = 0; r < LZ_TPT; r++) {
+						u32 ti = t0 + tid * LZ_TPT + r;
 						if (ti < ntok) {
 							u32 tk = tokbuf[ti];
 							if (tk & 0x80000000u) {
@@ -1335,8 +1606,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 							myval[r] = codes[256];
 						}
 					}
-					// CTA-wide exclusive scan of (mybits[0] + mybits[1])
-					u32 mine = mybits[0] + mybits[1];
+					// CTA-wide exclusive scan of the threads' bit counts
+					u32 mine = 0;
+#pragma unroll
+					for (int r = 0; r < LZ_TPT; r++) mine += mybits[r];
 					u32 incl = mine;
 					for (int o2 = 1; o2 < 32; o2 <<= 1) {
 						u32 t = __shfl_up_sync(LDB_FULL_MASK, incl, o2);
@@ -1356,8 +1629,11 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					}
 					__syncthreads();
 					u32 bitpos = rel + escan[32 + warp] + (incl - mine);
-					lz_stage_or(stage, bitpos, myval[0], mybits[0]);
-					lz_stage_or(stage, bitpos + mybits[0], myval[1], mybits[1]);
+#pragma unroll
+					for (int r = 0; r < LZ_TPT; r++) {
+						lz_stage_or(stage, bitpos, myval[r], mybits[r]);
+						bitpos += mybits[r];
+					}
 					const u32 round_bits = escan[64];
 					__syncthreads();
 					rel += round_bits;
@@ -1380,6 +1656,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			}
 			__syncthreads();
 			if (tid == 0) v->carry = stage[0];
+			LZ_T(6);	// costs + emission
 			// ---- next block ------------------------------------------------------------
 			block_begin = block_end;
 			block_entry = v->parse_entry;
@@ -1416,8 +1693,29 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			if (tid == 0) a.out_nbytes[c] = (size_t)(ob >> 3);
 		}
 		__syncthreads();
+		LZ_T(7);	// chunk prologue/epilogue
 	}
+#ifdef LZ_TIMING
+	if (tid == 0)
+		for (int k = 0; k < 15; k++) atomicAdd(&ldb_lz_timing[k], (unsigned long long)tacc[k]);
+#endif
 }
+
+#ifdef LZ_TIMING
+extern "C" __attribute__((visibility("default"))) void ldb_lz_timing_dump(void)
+{
+	unsigned long long h[16], z[16] = {};
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(h, ldb_lz_timing, sizeof(h));
+	cudaMemcpyToSymbol(ldb_lz_timing, z, sizeof(z));
+	const char *names[16] = {"loads+first", "search phase", "parse e5", "insert: linking", "huffman", "precode", "cost+emit", "chunk pro/epilogue",
+				 "parse e1", "parse e2", "parse e3", "parse e4", "insert: hashing", "insert: slice lists", "", ""};
+	unsigned long long tot = 0;
+	for (int k = 0; k < 14; k++) tot += h[k];
+	for (int k = 0; k < 16; k++)
+		if (h[k]) printf("  timing %-26s %14llu cycles  %5.1f%%\n", names[k], h[k], 100.0 * (double)h[k] / (double)tot);
+}
+#endif
 
 size_t ldb_deflate_scratch_bytes(const ldb_launch_cfg &cfg)
 {

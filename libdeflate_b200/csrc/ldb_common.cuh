@@ -13,6 +13,9 @@
 #define LDB_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
 #define LDB_LAUNCH(kernel, grid, block, smem, stream, ...) \
 	kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define LDB_SPIN_PAUSE() __nanosleep(100)
+#else
+#define LDB_SPIN_PAUSE() emu::yield()	// cooperative fibers: a spin loop must hand over
 #endif
 
 typedef uint8_t u8;

@@ -1,0 +1,13 @@
+mkdir -p gpurun_out
+for v in t1024r32 t1024r24 t1024r16 t512r32 tim1024r16 tim1024r32; do
+  echo "== $v"
+  timeout 300 python scripts/variant_bench.py $v roundtrip 16384 2> gpurun_out/var_$v.err | python -c "
+import sys, json
+for line in sys.stdin:
+    line = line.rstrip()
+    if line.startswith('{'):
+        d = json.loads(line); print(d['value'], d['kernel_ms_per_step'], d.get('verified'))
+    else:
+        print(line)
+"
+done

@@ -14,3 +14,7 @@ import bench  # noqa: E402
 a = argparse.Namespace(gpus=1, steps=3, warmup=3, impl="b200", workload=sys.argv[2] if len(sys.argv) > 2 else "decompress",
                        chunks=int(sys.argv[3]) if len(sys.argv) > 3 else 32768, chunk_size=65536, no_e2e=True, no_cpu=True)
 bench.run_b200(a)
+try:
+    ldb._lib.ldb_lz_timing_dump()
+except AttributeError:
+    pass
