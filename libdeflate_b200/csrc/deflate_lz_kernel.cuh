@@ -260,83 +260,8 @@ __device__ __forceinline__ void lz_flush_words(const lz_out &o, const u32 *stage
 }
 
 // ---- Huffman code construction ---------------------------------------------------------
-// lz_huffman_from_sorted: one thread; 'sorted' holds the nused used symbols in ascending
-// (freq, sym) order.  Scratch: nodefreq[2*nused] (u32), parent[2*nused] (u16).  Produces
-// lens[] limited to 'maxlen' bits (ref for the length-limiting idea:
-// deflate_compress.c:1023-1091; at least two codewords like deflate_compress.c:1369-1378).
-__device__ void lz_huffman_from_sorted(const u32 *freq, const u16 *sorted, u32 nused, u32 nsyms, u32 maxlen,
-				       u8 *lens, u32 *nodefreq, u16 *parent)
-{
-	for (u32 s = 0; s < nsyms; s++) lens[s] = 0;
-	if (nused == 0) {
-		lens[0] = 1;
-		lens[1] = 1;
-		return;
-	}
-	if (nused == 1) {
-		u32 s = sorted[0];
-		lens[s] = 1;
-		lens[s ? 0 : 1] = 1;
-		return;
-	}
-	// two-queue merge: leaves [0,nused) in sorted order, internal nodes appended after
-	for (u32 i = 0; i < nused; i++) nodefreq[i] = freq[sorted[i]];
-	u32 leaf = 0, inode = nused, nnodes = nused;
-	while (nnodes < 2 * nused - 1) {
-		u32 a, b;
-		if (leaf < nused && (inode >= nnodes || nodefreq[leaf] <= nodefreq[inode])) a = leaf++; else a = inode++;
-		if (leaf < nused && (inode >= nnodes || nodefreq[leaf] <= nodefreq[inode])) b = leaf++; else b = inode++;
-		nodefreq[nnodes] = nodefreq[a] + nodefreq[b];
-		parent[a] = (u16)nnodes;
-		parent[b] = (u16)nnodes;
-		nnodes++;
-	}
-	// depths: root is the last node; reuse nodefreq[] as depth for internal nodes
-	nodefreq[nnodes - 1] = 0;
-	for (u32 i = nnodes - 1; i-- > nused;) nodefreq[i] = nodefreq[parent[i]] + 1;
-	u32 count[17];
-	for (u32 l = 0; l <= 16; l++) count[l] = 0;
-	bool over = false;
-	for (u32 i = 0; i < nused; i++) {
-		u32 d = nodefreq[parent[i]] + 1;
-		if (d > maxlen) { d = maxlen; over = true; }
-		count[d]++;
-	}
-	if (over) {
-		// restore the Kraft sum to exactly 1 by lengthening the cheapest leaves
-		u32 kraft = 0;
-		for (u32 l = 1; l <= maxlen; l++) kraft += count[l] << (maxlen - l);
-		while (kraft > (1u << maxlen)) {
-			u32 l = maxlen - 1;
-			while (count[l] == 0) l--;
-			count[l]--;
-			count[l + 1] += 2;
-			count[maxlen]--;
-			kraft -= 1;
-		}
-	}
-	// hand out lengths: rarest symbols get the longest codes
-	u32 i = 0;
-	for (u32 l = maxlen; l >= 1; l--)
-		for (u32 k = 0; k < count[l]; k++) lens[sorted[i++]] = (u8)l;
-}
-
-// small alphabets (the precode): serial insertion sort, then the above
-__device__ void lz_build_huffman_small(const u32 *freq, u32 nsyms, u32 maxlen, u8 *lens, u16 *sorted, u32 *nodefreq, u16 *parent)
-{
-	u32 nused = 0;
-	for (u32 s = 0; s < nsyms; s++)
-		if (freq[s]) {
-			u32 j = nused++;
-			while (j > 0 && (freq[sorted[j - 1]] > freq[s])) {
-				sorted[j] = sorted[j - 1];
-				j--;
-			}
-			sorted[j] = (u16)s;
-		}
-	lz_huffman_from_sorted(freq, sorted, nused, nsyms, maxlen, lens, nodefreq, parent);
-}
-
+// (ref for the length-limiting idea: deflate_compress.c:1023-1091; at least two codewords like
+// deflate_compress.c:1369-1378; the parallel parts live in the kernel's build_codes step)
 // Two-queue Huffman merge only (one thread): leaves nodefreq[0, nused) ascending, internal nodes
 // appended behind them; writes parent[] for every node but the root.  The two queue heads and their
 // successors are kept in registers so that a shared-memory load is never waited for directly.
@@ -1424,27 +1349,81 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				if (tid == 0) v->n_items = ntot;
 			}
 			__syncthreads();
-			if (tid == 0) {
-				u32 pfreq[19];
-				for (int k = 0; k < 19; k++) pfreq[k] = pfreq_sm[k];
-				u8 plens[19];
-				u16 psorted[19];
-				u32 pnodef[38];
-				u16 ppar[38];
-				lz_build_huffman_small(pfreq, 19, 7, plens, psorted, pnodef, ppar);
+			if (warp == 0) {
+				// the 19-symbol precode, limited to 7 bits, by warp 0: lane = symbol.  Same construction
+				// as build_codes (rank sort, two-queue merge on lane 0, leaf depths, Kraft repair, lengths
+				// by rank, canonical codewords), with the counts per length packed into one u64.
+				u32 *pnodef = (u32 *)(sm + LZ_SM_GEXIT + 512);		// u32[38]
+				u16 *ppar = (u16 *)(sm + LZ_SM_GEXIT + 672);		// u16[38]
+				const u32 lt = (1u << lane) - 1;
+				const u32 f = lane < 19 ? pfreq_sm[lane] : 0;
+				const u32 usedm = __ballot_sync(LDB_FULL_MASK, f != 0);
+				const u32 nused = __popc(usedm);
+				u32 rank = 0;
+				for (u32 t = 0; t < 19; t++) {
+					const u32 ft = __shfl_sync(LDB_FULL_MASK, f, t);
+					rank += (ft != 0) && (ft < f || (ft == f && t < lane));
+				}
+				if (f) pnodef[rank] = f;
+				__syncwarp();
+				if (lane == 0 && nused >= 2) lz_huffman_merge(pnodef, ppar, nused);
+				__syncwarp();
+				u32 d = 0;
+				bool over = false;
+				if (f && nused >= 2) {
+					const u32 root = 2 * nused - 2;
+					u32 node = rank;
+					while (node != root && d <= 7) { node = ppar[node]; d++; }
+					if (d > 7) { d = 7; over = true; }
+				}
+				u64 cn = 0;		// codewords per length, 8 bits each
+				for (u32 l = 1; l <= 7; l++) cn |= (u64)__popc(__ballot_sync(LDB_FULL_MASK, d == l)) << (8 * l);
+				if (__any_sync(LDB_FULL_MASK, over)) {
+					u32 kraft = 0;
+					for (u32 l = 1; l <= 7; l++) kraft += (u32)((cn >> (8 * l)) & 0xff) << (7 - l);
+					while (kraft > (1u << 7)) {
+						u32 l = 6;
+						while (((cn >> (8 * l)) & 0xff) == 0) l--;
+						cn -= (u64)1 << (8 * l);
+						cn += (u64)2 << (8 * (l + 1));
+						cn -= (u64)1 << (8 * 7);
+						kraft -= 1;
+					}
+				}
+				u32 len = 0;
+				if (nused >= 2) {
+					if (f) {
+						u32 cum = 0;
+						len = 1;
+						for (u32 l = 7; l >= 1; l--) {
+							cum += (u32)((cn >> (8 * l)) & 0xff);
+							if (rank < cum) { len = l; break; }
+						}
+					}
+				} else {
+					// at least two codewords
+					const u32 sy = nused ? (u32)__ffs(usedm) - 1 : 0;
+					len = (lane == sy || lane == (sy ? 0u : 1u)) ? 1 : 0;
+					cn = (u64)2 << 8;
+				}
+				u32 first = 0;
+				for (u32 k = 1; k < len; k++) first = (first + (u32)((cn >> (8 * k)) & 0xff)) << 1;
+				const u32 samem = __match_any_sync(LDB_FULL_MASK, len);
+				const u32 code = len ? __brev(first + __popc(samem & lt)) >> (32 - len) : 0;
+				if (lane < 19) { plens_sm[lane] = (u8)len; pcodes_sm[lane] = (u16)code; }
+				__syncwarp();
 				const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-				u32 hclen = 19;
-				while (hclen > 4 && plens[perm[hclen - 1]] == 0) hclen--;
-				u32 cost = 3 + 5 + 5 + 4 + 3 * hclen;
-				for (int k = 0; k < 19; k++) cost += pfreq[k] * plens[k];
-				cost += 2 * pfreq[16] + 3 * pfreq[17] + 7 * pfreq[18];
-				v->cost_dyn = cost;
-				v->hclen = hclen;
-				u16 pcodes[19];
-				lz_gen_codes_serial(plens, 19, pcodes);
-				for (int k = 0; k < 19; k++) { plens_sm[k] = plens[k]; pcodes_sm[k] = pcodes[k]; }
-				v->cost_static = 3;
-				v->extra_bits = 0;
+				const u32 nzm = __ballot_sync(LDB_FULL_MASK, lane < 19 && plens_sm[perm[lane < 19 ? lane : 0]] != 0);
+				u32 hclen = nzm ? 32 - __clz(nzm) : 0;
+				if (hclen < 4) hclen = 4;
+				u32 cost = f * len + (lane == 16 ? 2 * f : lane == 17 ? 3 * f : lane == 18 ? 7 * f : 0);
+				for (int o2 = 16; o2 > 0; o2 >>= 1) cost += __shfl_xor_sync(LDB_FULL_MASK, cost, o2);
+				if (lane == 0) {
+					v->cost_dyn = cost + 3 + 5 + 5 + 4 + 3 * hclen;
+					v->hclen = hclen;
+					v->cost_static = 3;
+					v->extra_bits = 0;
+				}
 			}
 			__syncthreads();
 			LZ_T(5);	// precode
