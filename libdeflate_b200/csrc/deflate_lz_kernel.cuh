@@ -82,9 +82,8 @@
 #define LZ_BLOCK_POS (LZ_BLOCK_PASSES * LZ_PASS)		// positions per block
 #define LZ_OPT_K     8					// matches kept per position (levels 10-12)
 #define LZ_DP_SEG    2048				// positions per independent DP segment (one warp each)
-#define LZ_GS_RLEN   0						// u16[BLOCK_POS]  block-relative
-#define LZ_GS_ROFF   (LZ_GS_RLEN + 2 * LZ_BLOCK_POS)		// u16[BLOCK_POS]
-#define LZ_GS_EXIT   (LZ_GS_ROFF + 2 * LZ_BLOCK_POS)		// u16[PASS]       pass-relative
+#define LZ_GS_RES    0						// u32[BLOCK_POS]  block-relative
+#define LZ_GS_EXIT   (LZ_GS_RES + 4 * LZ_BLOCK_POS)		// u16[PASS]       pass-relative
 #define LZ_GS_TOK    (LZ_GS_EXIT + 2 * LZ_PASS)			// u32[TOKCAP]
 #define LZ_GS_COST   (LZ_GS_TOK + 4 * LZ_TOKCAP)		// u32[BLOCK_POS + 320]   (levels 10-12)
 #define LZ_GS_MLIST  (LZ_GS_COST + 4 * (LZ_BLOCK_POS + 320))	// u32[BLOCK_POS * K]     (levels 10-12)
@@ -317,6 +316,20 @@ __device__ unsigned long long ldb_lz_timing[16];
 #define LZ_T(k) do { } while (0)
 #endif
 
+// Lanes holding the same NBITS-bit key, from NBITS ballots (__match_any_sync gives the same mask
+// but takes several hundred cycles when most keys are distinct, which is the common case here).
+template <int NBITS>
+__device__ __forceinline__ u32 lz_same_key_mask(u32 key, bool valid)
+{
+	u32 m = __ballot_sync(LDB_FULL_MASK, valid);
+#pragma unroll
+	for (int b = 0; b < NBITS; b++) {
+		const u32 bal = __ballot_sync(LDB_FULL_MASK, (key >> b) & 1);
+		m &= ((key >> b) & 1) ? bal : ~bal;
+	}
+	return m;
+}
+
 // ---- ordered hash-chain insertion of one pass by the whole CTA -------------------------------
 // Chains must link every position to the previous one with the same hash, so insertion is ordered
 // -- but only within a hash value.  The head table is cut into LZ_NSL (16 or 32) slices by the top hash bits
@@ -327,9 +340,9 @@ __device__ unsigned long long ldb_lz_timing[16];
 //      slice list; the lists are packed into the 16 Ki next[] slots of the FOLLOWING pass, which
 //      belong to positions more than 48 Ki back -- outside every search window;
 //  (3) warp w re-walks its tiles in order and scatters the positions (rank inside a tile from
-//      __match_any_sync on the slice id): every list ends up sorted by position;
+//      the same-slice lane mask): every list ends up sorted by position;
 //  (4) warp s links list s, 32 entries at a time: predecessors inside the batch come from
-//      __match_any_sync on the hash, the others from head[].  Same links as a serial insertion.
+//      the same-hash lane mask, the others from head[].  Same links as a serial insertion.
 __device__ __forceinline__ void lz_insert_pass_par(const u8 *ring, u16 *head, u16 *nextt, u32 *cmat,
 						   u32 b0, u32 pend, u32 n, u32 tid, u32 lane, u32 warp
 #ifdef LZ_TIMING
@@ -374,7 +387,7 @@ __device__ __forceinline__ void lz_insert_pass_par(const u8 *ring, u16 *head, u1
 		const u32 hv = p < r1 ? nextt[p & 0xffff] : 0xffffu;
 		const bool valid = hv != 0xffffu;
 		const u32 sl = hv >> (LZ_HASH_BITS - LZ_NSL_BITS);
-		const u32 m = __match_any_sync(LDB_FULL_MASK, valid ? sl : (0x100u | lane));
+		const u32 m = lz_same_key_mask<LZ_NSL_BITS>(sl, valid);
 		const u32 cur = valid ? cmat[warp * LZ_NSL + sl] : 0;
 		__syncwarp();
 		if (valid) {
@@ -393,13 +406,13 @@ __device__ __forceinline__ void lz_insert_pass_par(const u8 *ring, u16 *head, u1
 		for (u32 b = 0; b < cnt; b += 32) {
 			const bool valid = b + lane < cnt;
 			const u32 p16 = p16n;
-			const u32 h = valid ? hn : (0x10000u | lane);
+			const u32 h = valid ? hn : 0;
 			if (b + 32 + lane < cnt) {		// next batch: list entry and parked hash
 				p16n = mylist[b + 32 + lane];
 				hn = nextt[p16n];
 			}
 			const u32 old_head = valid ? head[h] : 0;
-			const u32 m = __match_any_sync(LDB_FULL_MASK, h);
+			const u32 m = lz_same_key_mask<LZ_HASH_BITS - LZ_NSL_BITS>(h, valid);	// (the slice bits are equal anyway)
 			const u32 below = m & lt;
 			const u32 prev = __shfl_sync(LDB_FULL_MASK, p16, below ? 31 - __clz(below) : 0);
 			if (valid) {
@@ -515,8 +528,8 @@ __device__ __forceinline__ void lz_search_all(const u8 *ring, const u16 *nextt, 
 // 32 shortest candidate lengths need no memory at all; longer ones read the cost array.  A path
 // never crosses s1 (segments are independent; the price is one constrained token per 2048
 // positions).  The decision is written as a (length | flag, distance) pair the parallel parser
-// then follows: rlen = L (0 for a literal), roff = dist-1 | 0x8000.
-__device__ void lz_dp_segment(const u8 *ring, const u32 *mlist, u32 *costg, u16 *rlen, u16 *roff, const u8 *costtab,
+// then follows: res = L | (dist-1 | 0x8000) << 16 (0 for a literal).
+__device__ void lz_dp_segment(const u8 *ring, const u32 *mlist, u32 *costg, u32 *res, const u8 *costtab,
 			      u32 block_begin, u32 s0, u32 s1, u32 lane)
 {
 	const u8 *litc = costtab, *lenc = costtab + 256, *offc = costtab + 256 + 259;
@@ -583,11 +596,9 @@ __device__ void lz_dp_segment(const u8 *ring, const u32 *mlist, u32 *costg, u16 
 			if (lane == 0) {
 				costg[pos] = C;
 				if (bestL >= 3) {
-					rlen[pos] = (u16)bestL;
-					roff[pos] = (u16)((dist_for(bestL) - 1) | 0x8000);
+					res[pos] = bestL | (((dist_for(bestL) - 1) | 0x8000u) << 16);
 				} else {
-					rlen[pos] = 0;
-					roff[pos] = 0;
+					res[pos] = 0;
 				}
 			}
 			const u32 t = __shfl_up_sync(LDB_FULL_MASK, wc, 1);
@@ -627,8 +638,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 	u16 *items = (u16 *)(sm + LZ_SM_ITEMS);				// precode items (<= 320 + slack)
 	// per-position results of the current pass live in this CTA's global scratch
 	u8 *gs = a.scratch + (size_t)blockIdx.x * LZ_GS_BYTES;
-	u16 *rlen = (u16 *)(gs + LZ_GS_RLEN);
-	u16 *roff = (u16 *)(gs + LZ_GS_ROFF);
+	u32 *res = (u32 *)(gs + LZ_GS_RES);	// per position: match length | (distance-1 | decision flag << 15) << 16
 	u16 *exitt = (u16 *)(gs + LZ_GS_EXIT);
 	u32 *tokbuf = (u32 *)(gs + LZ_GS_TOK);
 	u32 *costg = (u32 *)(gs + LZ_GS_COST);
@@ -719,28 +729,29 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		o.obit = (u64)hdr_bytes * 8;
 		__syncthreads();
 
-		// ---- exact parallel parse of one pass (positions [pb0, ppend), results at rlen/roff[aoff + i]).
+		// ---- exact parallel parse of one pass (positions [pb0, ppend), results at res[aoff + i]).
 		// forced: the DP already decided (flag set on matches); otherwise the lazy rule decides.
 		auto parse_pass = [&](const u32 pb0, const u32 ppend, const u32 aoff, const bool forced) {
 			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
 			const u32 nwin = (ppend - pb0 + 31) >> 5;
 			// (the loads of the next window are issued before the current one is processed)
 			const u32 min_len = v->min_len;
-			u32 nL0 = 0, nR0 = 0, nL1 = 0, nR1 = 0;
+			u32 nW0 = 0, nW1 = 0;
 			if (warp < nwin) {
 				u32 i = warp * 32 + lane;
-				if (pb0 + i < ppend) { nL0 = rlen[aoff + i]; nR0 = roff[aoff + i]; }
-				if (pb0 + i + 1 < ppend) { nL1 = rlen[aoff + i + 1]; nR1 = roff[aoff + i + 1]; }
+				if (pb0 + i < ppend) nW0 = res[aoff + i];
+				if (lane == 31 && pb0 + i + 1 < ppend) nW1 = res[aoff + i + 1];	// (the others get it by shuffle)
 			}
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				u32 i = w * 32 + lane;
 				u32 p = pb0 + i;
-				const u32 L0 = nL0, O0 = (nR0 & 0x7fff) + 1, L1 = nL1, O1 = (nR1 & 0x7fff) + 1;
+				const u32 W0 = nW0, nb = __shfl_down_sync(LDB_FULL_MASK, W0, 1), W1 = lane == 31 ? nW1 : nb;
+				const u32 L0 = W0 & 0xffff, O0 = ((W0 >> 16) & 0x7fff) + 1, L1 = W1 & 0xffff, O1 = ((W1 >> 16) & 0x7fff) + 1;
 				if (w + LZ_WARPS < nwin) {
 					u32 i2 = i + LZ_WARPS * 32;
-					nL0 = 0; nR0 = 0; nL1 = 0; nR1 = 0;
-					if (pb0 + i2 < ppend) { nL0 = rlen[aoff + i2]; nR0 = roff[aoff + i2]; }
-					if (pb0 + i2 + 1 < ppend) { nL1 = rlen[aoff + i2 + 1]; nR1 = roff[aoff + i2 + 1]; }
+					nW0 = 0; nW1 = 0;
+					if (pb0 + i2 < ppend) nW0 = res[aoff + i2];
+					if (lane == 31 && pb0 + i2 + 1 < ppend) nW1 = res[aoff + i2 + 1];
 				}
 				bool is_match = forced ? ((L0 >= 3) && p < ppend) : (L0 >= min_len && p < ppend);
 				if (!forced && is_match && P.lazy && p + 1 < ppend) {
@@ -750,10 +761,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						is_match = false;
 				}
 				u32 step = is_match ? L0 : 1;
-				// decision flag in the top bit; the neighbour that reads roff[aoff + i] for its lazy test
+				// decision flag in the top bit; the neighbour that reads res[aoff + i] for its lazy test
 				// masks it off, and it only reads -- the flag is published after this warp's reads
 				__syncwarp();
-				if (is_match && !forced) roff[aoff + i] = (u16)((O0 - 1) | 0x8000);
+				if (is_match && !forced) res[aoff + i] = L0 | (((O0 - 1) | 0x8000u) << 16);
 				u32 j = lane + step;
 #pragma unroll
 				for (int k = 0; k < 5; k++) {
@@ -849,23 +860,23 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			__syncthreads();
 			LZ_T(9);
 			// (e3) visited sets per window (the loads of the next window are issued first)
-			u32 e3_e = 0xff, e3_ro = 0, e3_rl = 0;
+			u32 e3_e = 0xff, e3_w = 0;
 			if (warp < nwin) {
 				const u32 i = warp * 32 + lane;
 				e3_e = entryt[warp];
-				if (e3_e != 0xff && pb0 + i < ppend) { e3_ro = roff[aoff + i]; e3_rl = rlen[aoff + i]; }
+				if (e3_e != 0xff && pb0 + i < ppend) e3_w = res[aoff + i];
 			}
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
-				const u32 e = e3_e, ro = e3_ro, rl = e3_rl;
+				const u32 e = e3_e, rw = e3_w;
 				if (w + LZ_WARPS < nwin) {
 					const u32 i2 = (w + LZ_WARPS) * 32 + lane;
 					e3_e = entryt[w + LZ_WARPS];
-					e3_ro = 0; e3_rl = 0;
-					if (e3_e != 0xff && pb0 + i2 < ppend) { e3_ro = roff[aoff + i2]; e3_rl = rlen[aoff + i2]; }
+					e3_w = 0;
+					if (e3_e != 0xff && pb0 + i2 < ppend) e3_w = res[aoff + i2];
 				}
 				u32 V = 0;
 				if (e != 0xff) {
-					u32 step = (ro & 0x8000) ? rl : 1;
+					u32 step = (rw & 0x80000000u) ? (rw & 0xffff) : 1;
 					u32 j = lane + step;
 					u32 jk[5];
 #pragma unroll
@@ -908,19 +919,19 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			LZ_T(11);
 			// (e5) emit tokens + histograms
 			const u32 tbase = v->tok_count;
-			u32 e5_V = 0, e5_ro = 0, e5_rl = 0;
+			u32 e5_V = 0, e5_w = 0;
 			if (warp < nwin) {
 				const u32 i = warp * 32 + lane;
 				e5_V = vis[warp];
-				if ((e5_V >> lane) & 1) { e5_ro = roff[aoff + i]; e5_rl = rlen[aoff + i]; }
+				if ((e5_V >> lane) & 1) e5_w = res[aoff + i];
 			}
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
-				const u32 V = e5_V, ro = e5_ro;
-				const u32 len = e5_rl;
+				const u32 V = e5_V, ro = e5_w >> 16;
+				const u32 len = e5_w & 0xffff;
 				if (w + LZ_WARPS < nwin) {
 					const u32 i2 = (w + LZ_WARPS) * 32 + lane;
 					e5_V = vis[w + LZ_WARPS];
-					if ((e5_V >> lane) & 1) { e5_ro = roff[aoff + i2]; e5_rl = rlen[aoff + i2]; }
+					if ((e5_V >> lane) & 1) e5_w = res[aoff + i2];
 				}
 				if (!V) continue;
 				u32 i = w * 32 + lane;
@@ -1117,7 +1128,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// chosen match covers (they inherit it at the same distance).  Every position
 				// still gets a (length, distance), so the exact parallel parse below can start a
 				// token anywhere.  One search call site per loop trip keeps the warp converged.
-				u16 *rl = rlen + pass_in_block * LZ_PASS, *rf = roff + pass_in_block * LZ_PASS;
+				u32 *rs = res + pass_in_block * LZ_PASS;
 				if (P.opt_iters) {
 					// levels 10-12: every position is searched and keeps its list of matches
 					for (u32 i = tid; b0 + i < pend; i += LZ_THREADS) {
@@ -1129,8 +1140,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						} else {
 							for (u32 k = 0; k < LZ_OPT_K; k++) ml[k] = 0;
 						}
-						rl[i] = (u16)L;
-						rf[i] = (u16)(L ? D - 1 : 0);
+						rs[i] = L ? L | ((D - 1) << 16) : 0;
 					}
 				} else {
 				const u32 min_len = v->min_len;
@@ -1157,8 +1167,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						if (pending) { L = pL - 1 >= 4 ? pL - 1 : 0; D = pD; }
 						lz_search(ring, nextt, p, n, pending ? (P.depth >> 1) : P.depth, (u32)P.nice, L, D);
 					}
-					rl[i] = (u16)L;
-					rf[i] = (u16)(L ? D - 1 : 0);
+					rs[i] = L ? L | ((D - 1) << 16) : 0;
 					u32 mpos, mL, mD;	// match to accept this trip (mL == 0: none)
 					if (pending) {
 						if (L >= pL && 4 * ((int)L - (int)pL) + ((int)(31 - __clz((int)pD)) - (int)(31 - __clz((int)D))) > 2) {
@@ -1190,10 +1199,11 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						u32 mend = b0 + mpos + mL;
 						for (u32 k = i + 1; k < stop; k++) {
 							const u32 pk = b0 + k;
-							while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - mD)) mend++;
+							// (the match ended on a mismatch unless it was capped at 258 bytes)
+							if (mL == 258)
+								while (mend < n && mend - pk < 258 && lz_ld8(ring, mend) == lz_ld8(ring, mend - mD)) mend++;
 							u32 lk = mend - pk;
-							rl[k] = (u16)(lk >= 4 ? lk : 0);
-							rf[k] = (u16)(lk >= 4 ? mD - 1 : 0);
+							rs[k] = lk >= 4 ? lk | ((mD - 1) << 16) : 0;
 						}
 						i = mpos + mL;
 					} else {
@@ -1245,7 +1255,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						u32 s0 = seg * LZ_DP_SEG, s1 = s0 + LZ_DP_SEG < blen_pos ? s0 + LZ_DP_SEG : blen_pos;
 						if (s0 < rel_entry) s0 = rel_entry;
 						if (s0 >= s1) continue;
-						lz_dp_segment(ring, mlist, costg, rlen, roff, costtab, block_begin, s0, s1, lane);
+						lz_dp_segment(ring, mlist, costg, res, costtab, block_begin, s0, s1, lane);
 					}
 				}
 				__syncthreads();

@@ -90,7 +90,10 @@
 #define INF_SM_CNT     (INF_SM_SCRATCH)				// u32[16]
 #define INF_SM_CODE    (INF_SM_CNT + 64)			// u32[16]
 #define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[1 << INF_LB]
-#define INF_SM_BYTES   (INF_SM_SUBBITS + (1 << INF_LB))		// 49792 with the default geometry
+#define INF_SM_BYTES   (INF_SM_SUBBITS + (1 << INF_LB))		// per warp: 14592 with the default geometry
+#ifndef INF_WPC
+#define INF_WPC        5		// independent warps per CTA
+#endif
 
 static_assert(INF_L_ENTRIES >= 160, "the litlen region doubles as the 320-byte code-length scratch");
 static_assert(INF_O_ENTRIES >= 64, "the offset region doubles as the 128-byte precode table scratch");
@@ -768,12 +771,17 @@ __device__ __forceinline__ int inf_decode_offset(inf_lane &s, const u8 *sm, cons
 }
 
 // ---- the kernel ---------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+// The warps of a CTA are independent (each has its own tables and never syncs with the others);
+// INF_WPC of them share a CTA only because shared memory is reserved per CTA (1 KiB each), and
+// 3 CTAs x 5 warps fit where 15 single-warp CTAs would not.
+__global__ void __launch_bounds__(32 * INF_WPC)
 ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 {
-	LDB_DYN_SMEM(sm);
+	LDB_DYN_SMEM(sm_cta);
+	u8 *sm = sm_cta + (threadIdx.x >> 5) * INF_SM_BYTES;
 	const u32 lane = threadIdx.x & 31;
-	u16 *ovf = (u16 *)a.overflow_scratch + ((size_t)blockIdx.x * 32 + lane) * INF_OVF_ENTRIES;
+	const size_t gwarp = (size_t)blockIdx.x * INF_WPC + (threadIdx.x >> 5);	// global warp index
+	u16 *ovf = (u16 *)a.overflow_scratch + (gwarp * 32 + lane) * INF_OVF_ENTRIES;
 
 	inf_lane s;
 	s.state = ST_IDLE;
@@ -907,7 +915,7 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 			}
 			ol[0] = is_static ? 5u : (lane < hdist ? lens[scr_idx(hlit + lane, owner)] : 0);
 			__syncwarp();
-			u16 *ovf_owner = (u16 *)a.overflow_scratch + ((size_t)blockIdx.x * 32 + owner) * INF_OVF_ENTRIES;
+			u16 *ovf_owner = (u16 *)a.overflow_scratch + (gwarp * 32 + owner) * INF_OVF_ENTRIES;
 			// offset code first, like the reference (decompress_template.h:331-332)
 			bool ok = inf_build_table<1, INF_OB, INF_OSUB_SM, INF_OSUB_CAP, false>(ol, sm, INF_SM_OTAB, ovf_owner + INF_OVF_L, owner, lane);
 			ok = ok && inf_build_table<9, INF_LB, INF_LSUB_SM, INF_LSUB_CAP, true>(ll, sm, INF_SM_LTAB, ovf_owner, owner, lane);
@@ -971,24 +979,26 @@ int ldb_launch_inflate(const ldb_inflate_args &a, const ldb_launch_cfg &cfg, voi
 	if (a.n == 0) return 0;
 	static bool attr_set = false;
 	if (!attr_set) {
-		LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SM_BYTES));
+		LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_WPC * INF_SM_BYTES));
 		attr_set = true;
 	}
 	u32 *counter = (u32 *)(a.overflow_scratch + (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream());
 	LDB_CUDA_CHECK_RET(cudaMemsetAsync(counter, 0, sizeof(u32), (cudaStream_t)stream));
-	size_t blocks = (a.n + 31) / 32;
-	size_t cap = (size_t)ldb_inflate_grid_blocks(cfg);
+	size_t blocks = (a.n + 32 * INF_WPC - 1) / (32 * INF_WPC);
+	size_t cap = (size_t)ldb_inflate_grid_blocks(cfg) / INF_WPC;
 	if (blocks > cap) blocks = cap;
-	LDB_LAUNCH(ldb_inflate_kernel, dim3((unsigned)blocks), dim3(32), INF_SM_BYTES, (cudaStream_t)stream, a, counter);
+	LDB_LAUNCH(ldb_inflate_kernel, dim3((unsigned)blocks), dim3(32 * INF_WPC), INF_WPC * INF_SM_BYTES, (cudaStream_t)stream, a, counter);
 	LDB_CUDA_CHECK_RET(cudaGetLastError());
 	return 0;
 }
 
+// Number of WARPS (= groups of 32 concurrently decoded streams) the launch keeps resident.
 int ldb_inflate_grid_blocks(const ldb_launch_cfg &cfg)
 {
-	int per_sm = cfg.max_smem_optin / (INF_SM_BYTES + 1024);
-	if (per_sm < 1) per_sm = 1;
-	return cfg.num_sms * per_sm;
+	// shared memory per SM is the opt-in per-CTA maximum + 1 KiB; every CTA reserves 1 KiB
+	int ctas_per_sm = (cfg.max_smem_optin + 1024) / (INF_WPC * INF_SM_BYTES + 1024);
+	if (ctas_per_sm < 1) ctas_per_sm = 1;
+	return cfg.num_sms * ctas_per_sm * INF_WPC;
 }
 
 size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg)

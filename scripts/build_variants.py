@@ -13,12 +13,8 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    "t1024r32": ["-DLZ_THREADS=1024", "-DLZ_RUN=32"],
-    "t1024r24": ["-DLZ_THREADS=1024", "-DLZ_RUN=24"],
-    "t1024r16": ["-DLZ_THREADS=1024", "-DLZ_RUN=16"],
-    "t512r32": ["-DLZ_THREADS=512", "-DLZ_RUN=32"],
-    "tim1024r16": ["-DLZ_TIMING", "-DLZ_THREADS=1024", "-DLZ_RUN=16"],
-    "tim1024r32": ["-DLZ_TIMING", "-DLZ_THREADS=1024", "-DLZ_RUN=32"],
+    "cur": [],
+    "curtim": ["-DLZ_TIMING"],
 }
 
 

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in t1024r32 t1024r24 t1024r16 t512r32 tim1024r16 tim1024r32; do
+for v in cur curtim; do
   echo "== $v"
   timeout 300 python scripts/variant_bench.py $v roundtrip 16384 2> gpurun_out/var_$v.err | python -c "
 import sys, json
