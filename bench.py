@@ -423,16 +423,25 @@ def run_b200(args):
     # deflate = uncompressed in + compressed out
     alg_inf = comp_bytes + n * chunk
     alg_def = n * chunk + comp_bytes
+    traffic_key = "%s_L%d_%dx%d" % (args.workload, LEVEL, n, chunk)
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(traffic_key, {})
+    except Exception:
+        traffic_db = {}
+
     def roof(t, cnt, alg, name):
         if cnt == 0 or t <= 0:
             return None
         per = t / cnt / 1e3
         ach = alg / per / 1e9
+        tr = traffic_db.get(name, {}).get("dram_bytes_per_launch")
         return {"kernel": name, "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4), "traffic": int(tr) if tr else None,
+                "traffic_source": ("profiles/dram_traffic.json[%s] (ncu dram__bytes_read+write, same configuration)" % traffic_key) if tr else None,
+                "peak_source": peak_src,
                 "avg_launch_ms": round(per * 1e3, 4), "algorithmic_bytes_per_launch": int(alg)}
     r_inf = roof(t_inf, n_inf, alg_inf, "ldb_inflate_kernel")
-    r_def = roof(t_def, n_def, alg_def, "ldb_deflate_kernel")
+    r_def = roof(t_def, n_def, alg_def, "ldb_deflate_lz_kernel")
     dominant = r_def if (r_def and t_def >= t_inf) else r_inf
     line = {
         "metric": metric_name(args), "value": round(value, 2), "unit": "MB/s", "n_gpus": world,

@@ -127,8 +127,8 @@ __device__ __forceinline__ lz_params lz_level_params(int level)
 	case 5: return {12, 48, 1, 0};
 	case 6: return {24, 96, 1, 0};
 	case 7: return {48, 160, 1, 0};
-	case 8: return {96, 258, 1, 0};
-	case 9: return {200, 258, 1, 0};
+	case 8: return {96, 258, 2, 0};		// lazy2: one more position of lookahead (ref: deflate_compress.c:2742-2776)
+	case 9: return {200, 258, 2, 0};
 	// near-optimal levels (ref: lib/deflate_compress.c:3972-4012: depth 35/100/300, passes 2/4/10)
 	case 10: return {48, 96, 1, 2};
 	case 11: return {96, 160, 1, 3};
@@ -736,22 +736,25 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			const u32 nwin = (ppend - pb0 + 31) >> 5;
 			// (the loads of the next window are issued before the current one is processed)
 			const u32 min_len = v->min_len;
-			u32 nW0 = 0, nW1 = 0;
+			u32 nW0 = 0, nW1 = 0, nW2 = 0;
 			if (warp < nwin) {
 				u32 i = warp * 32 + lane;
 				if (pb0 + i < ppend) nW0 = res[aoff + i];
 				if (lane == 31 && pb0 + i + 1 < ppend) nW1 = res[aoff + i + 1];	// (the others get it by shuffle)
+				if (lane == 31 && P.lazy == 2 && pb0 + i + 2 < ppend) nW2 = res[aoff + i + 2];
 			}
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				u32 i = w * 32 + lane;
 				u32 p = pb0 + i;
 				const u32 W0 = nW0, nb = __shfl_down_sync(LDB_FULL_MASK, W0, 1), W1 = lane == 31 ? nW1 : nb;
+				const u32 nb2 = __shfl_down_sync(LDB_FULL_MASK, W1, 1), W2 = lane == 31 ? nW2 : nb2;	// two ahead (lazy2)
 				const u32 L0 = W0 & 0xffff, O0 = ((W0 >> 16) & 0x7fff) + 1, L1 = W1 & 0xffff, O1 = ((W1 >> 16) & 0x7fff) + 1;
 				if (w + LZ_WARPS < nwin) {
 					u32 i2 = i + LZ_WARPS * 32;
-					nW0 = 0; nW1 = 0;
+					nW0 = 0; nW1 = 0; nW2 = 0;
 					if (pb0 + i2 < ppend) nW0 = res[aoff + i2];
 					if (lane == 31 && pb0 + i2 + 1 < ppend) nW1 = res[aoff + i2 + 1];
+					if (lane == 31 && P.lazy == 2 && pb0 + i2 + 2 < ppend) nW2 = res[aoff + i2 + 2];
 				}
 				bool is_match = forced ? ((L0 >= 3) && p < ppend) : (L0 >= min_len && p < ppend);
 				if (!forced && is_match && P.lazy && p + 1 < ppend) {
@@ -759,6 +762,13 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					if (L1 >= L0 && L0 < (u32)P.nice &&
 					    4 * ((int)L1 - (int)L0) + ((int)(31 - __clz((int)O0)) - (int)(31 - __clz((int)O1))) > 2)
 						is_match = false;
+					if (P.lazy == 2 && is_match && p + 2 < ppend) {
+						// ref: deflate_compress.c:2757-2760 -- or the one after it, by a wider margin
+						const u32 L2 = W2 & 0xffff, O2 = ((W2 >> 16) & 0x7fff) + 1;
+						if (L2 >= L0 && L0 < (u32)P.nice &&
+						    4 * ((int)L2 - (int)L0) + ((int)(31 - __clz((int)O0)) - (int)(31 - __clz((int)O2))) > 6)
+							is_match = false;
+					}
 				}
 				u32 step = is_match ? L0 : 1;
 				// decision flag in the top bit; the neighbour that reads res[aoff + i] for its lazy test
@@ -1151,38 +1161,43 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
 				// (long matches, few searches) take more of them, which keeps the warp busy
 				u32 i = 0, i_end = 0;
-				u32 pL = 0, pD = 0;		// pending match at position i-1 (lazy evaluation in progress)
-				bool pending = false;
+				u32 pL = 0, pD = 0;		// pending match at position i-pending (lazy evaluation in progress)
+				u32 pending = 0;		// 0: none, 1: looking one position ahead, 2: two positions (lazy2)
 				for (;;) {
 					if (i >= i_end || b0 + i >= pend) {
 						const u32 r = atomicAdd(&v->run_counter, 1u);
 						i = r * run_len;
 						if (b0 + i >= pend || i >= LZ_PASS) break;
 						i_end = i + run_len;
-						pending = false;
+						pending = 0;
 					}
 					const u32 p = b0 + i;
 					u32 L = 0, D = 0;
 					if (p + 4 <= n) {
-						if (pending) { L = pL - 1 >= 4 ? pL - 1 : 0; D = pD; }
-						lz_search(ring, nextt, p, n, pending ? (P.depth >> 1) : P.depth, (u32)P.nice, L, D);
+						if (pending) { L = pL - pending >= 4 ? pL - pending : 0; D = pD; }	// the pending match continues here
+						lz_search(ring, nextt, p, n, P.depth >> pending, (u32)P.nice, L, D);
 					}
 					rs[i] = L ? L | ((D - 1) << 16) : 0;
 					u32 mpos, mL, mD;	// match to accept this trip (mL == 0: none)
 					if (pending) {
-						if (L >= pL && 4 * ((int)L - (int)pL) + ((int)(31 - __clz((int)pD)) - (int)(31 - __clz((int)D))) > 2) {
-							// the lookahead match is clearly better: literal at i-1, keep looking
+						// ref: deflate_compress.c:2722-2725 (margin 2, one ahead), :2757-2760 (margin 6, two ahead)
+						const int margin = pending == 1 ? 2 : 6;
+						if (L >= pL && 4 * ((int)L - (int)pL) + ((int)(31 - __clz((int)pD)) - (int)(31 - __clz((int)D))) > margin) {
+							// the lookahead match is clearly better: literal(s) before i, keep looking
 							// ahead from i unless it is long enough to take at once
 							mpos = i; mL = L >= (u32)P.nice ? L : 0; mD = D;
 							if (!mL) { pL = L; pD = D; }
-							pending = mL == 0;
+							pending = mL == 0 ? 1 : 0;
+						} else if (pending == 1 && P.lazy == 2 && i + 1 < i_end && b0 + i + 1 < pend) {
+							pending = 2;
+							mpos = i; mL = 0; mD = 0;
 						} else {
-							mpos = i - 1; mL = pL; mD = pD;
-							pending = false;
+							mpos = i - pending; mL = pL; mD = pD;
+							pending = 0;
 						}
 					} else if (L >= min_len) {
 						if (P.lazy && L < (u32)P.nice && i + 1 < i_end && b0 + i + 1 < pend) {
-							pending = true; pL = L; pD = D;
+							pending = 1; pL = L; pD = D;
 							mpos = i; mL = 0; mD = 0;
 						} else {
 							mpos = i; mL = L; mD = D;
