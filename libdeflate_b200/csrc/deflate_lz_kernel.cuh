@@ -49,6 +49,9 @@
 #define LZ_NWIN      (LZ_PASS / 32)
 #define LZ_NSL_BITS  (LZ_WARPS >= 32 ? 5 : 4)	// hash slices of the insertion = linking warps
 #define LZ_NSL       (1 << LZ_NSL_BITS)
+#ifndef LZ_TRIPS
+#define LZ_TRIPS     4			// loop trips (= searches) a thread spends on a run per round
+#endif
 #define LZ_SEG       16384			// largest single TMA load
 #define LZ_RING      65536
 #define LZ_HASH_BITS 13
@@ -1157,20 +1160,35 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// A run starts its walk without knowing where the parse really enters it, so short
 				// runs cost a little ratio (L6: +0.9 % at 16 vs 32) and buy parallelism; the deep
 				// levels, which are chosen for ratio, keep 32.
-				const u32 run_len = a.level >= 7 ? 32 : 16;
-				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
-				// (long matches, few searches) take more of them, which keeps the warp busy
+				const u32 run_len = (a.level >= 7 || LZ_PASS / 16 > LZ_THREADS) ? 32 : 16;
+				// A run takes between ~2 trips of the loop below (long matches) and run_len trips (all
+				// literals), one search per trip.  To keep the lanes of a warp alive together, a thread
+				// works on a run for at most LZ_TRIPS trips per round; unfinished runs are queued with
+				// their (tiny) walk state and dealt out again, densely packed, in the next round.  Who
+				// continues a run does not matter, so the result is deterministic.
+				const u32 nruns = (pend - b0 + run_len - 1) / run_len;
+				u32 *qlist = (u32 *)(sm + LZ_SM_R);		// 2 words per queued run (<= 8 KiB)
+				u32 nitems = nruns;
+				for (u32 round = 0; nitems; round++) {
 				u32 i = 0, i_end = 0;
 				u32 pL = 0, pD = 0;		// pending match at position i-pending (lazy evaluation in progress)
 				u32 pending = 0;		// 0: none, 1: looking one position ahead, 2: two positions (lazy2)
-				for (;;) {
-					if (i >= i_end || b0 + i >= pend) {
-						const u32 r = atomicAdd(&v->run_counter, 1u);
-						i = r * run_len;
-						if (b0 + i >= pend || i >= LZ_PASS) break;
-						i_end = i + run_len;
-						pending = 0;
+				const bool have = tid < nitems;
+				if (have) {
+					if (round == 0) {
+						i = tid * run_len;
+						i_end = i + run_len < pend - b0 ? i + run_len : pend - b0;
+					} else {
+						const u32 q0 = qlist[2 * tid], q1 = qlist[2 * tid + 1];
+						i = q0 & 0xffff; i_end = q0 >> 16;
+						pending = q1 >> 30; pL = (q1 >> 15) & 0x1ff; pD = q1 & 0x7fff;
 					}
+				}
+				__syncthreads();
+				if (tid == 0) v->run_counter = 0;	// tail of the queue being filled
+				__syncthreads();
+				if (have) {
+				for (u32 trip = 0; trip < LZ_TRIPS && i < i_end; trip++) {
 					const u32 p = b0 + i;
 					u32 L = 0, D = 0;
 					if (p + 4 <= n) {
@@ -1225,6 +1243,15 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						i++;
 					}
 				}
+				if (i < i_end) {
+					const u32 k = atomicAdd(&v->run_counter, 1u);
+					qlist[2 * k] = i | (i_end << 16);
+					qlist[2 * k + 1] = (pending << 30) | (pL << 15) | pD;
+				}
+				}	// have
+				__syncthreads();
+				nitems = v->run_counter;
+				}	// rounds
 				}	// guided search (levels 1-9)
 			}
 			__syncthreads();

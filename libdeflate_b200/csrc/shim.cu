@@ -601,12 +601,15 @@ static void pipe_events_destroy(pipe_events *e)
 {
 	for (int i = 0; i < e->n; i++) { cudaEventDestroy(e->in[i]); cudaEventDestroy(e->done[i]); }
 }
-static size_t pipe_stages(size_t n, size_t total_bytes)
+// min_chunks: smallest sub-batch that still fills the kernel of this direction (the inflate kernel
+// decodes one chunk per lane, ~71 K lanes resident; the deflate kernel one chunk per CTA)
+static size_t pipe_stages(size_t n, size_t total_bytes, size_t min_chunks)
 {
 	size_t s = total_bytes / ((size_t)256 << 20);
+	if (const char *e = getenv("LIBDEFLATE_B200_PIPE_STAGES")) s = (size_t)atoi(e);
 	if (s < 2) s = 2;
 	if (s > LDB_PIPE_MAX_STAGES) s = LDB_PIPE_MAX_STAGES;
-	if (s > n / 256) s = n / 256 ? n / 256 : 1;
+	if (s > n / min_chunks) s = n / min_chunks ? n / min_chunks : 1;
 	return s;
 }
 
@@ -639,7 +642,7 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 	if (!rc && pipelined) {
 		host_span isp = span_of(h_in, h_in_nbytes, n, false), osp = span_of((const void *const *)h_out, h_out_avail, n, true);
 		const size_t imis = (uintptr_t)isp.lo & 15, omis = (uintptr_t)osp.lo & 15;
-		const size_t S = pipe_stages(n, (size_t)(isp.hi - isp.lo) + (size_t)(osp.hi - osp.lo));
+		const size_t S = pipe_stages(n, (size_t)(isp.hi - isp.lo) + (size_t)(osp.hi - osp.lo), 16384);
 		pipe_events ev;
 		rc = pipe_events_create(&ev, (int)S);
 		for (size_t k = 0; k < S && !rc; k++) {
@@ -726,7 +729,7 @@ extern "C" int libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *c
 	if (!rc && pipelined) {
 		host_span isp = span_of(h_in, h_in_nbytes, n, false), osp = span_of((const void *const *)h_out, h_out_avail, n, true);
 		const size_t imis = (uintptr_t)isp.lo & 15, omis = (uintptr_t)osp.lo & 15;
-		const size_t S = pipe_stages(n, (size_t)(isp.hi - isp.lo) + (size_t)(osp.hi - osp.lo));
+		const size_t S = pipe_stages(n, (size_t)(isp.hi - isp.lo) + (size_t)(osp.hi - osp.lo), 1024);
 		pipe_events ev;
 		rc = pipe_events_create(&ev, (int)S);
 		for (size_t k = 0; k < S && !rc; k++) {
