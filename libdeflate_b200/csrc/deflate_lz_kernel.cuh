@@ -49,9 +49,6 @@
 #define LZ_NWIN      (LZ_PASS / 32)
 #define LZ_NSL_BITS  (LZ_WARPS >= 32 ? 5 : 4)	// hash slices of the insertion = linking warps
 #define LZ_NSL       (1 << LZ_NSL_BITS)
-#ifndef LZ_TRIPS
-#define LZ_TRIPS     4			// loop trips (= searches) a thread spends on a run per round
-#endif
 #define LZ_SEG       16384			// largest single TMA load
 #define LZ_RING      65536
 #define LZ_HASH_BITS 13
@@ -107,6 +104,8 @@ struct lz_vars {
 	u32 carry;		// partial output word at bit position obit (persists between flushes)
 	u32 nused_lit, nused_off;
 	u32 huff_over;		// a Huffman code exceeded 15 bits and was capped
+	u32 obs_blk[8], obs_next[8];	// byte-class observations: current block / the pass after it
+	u32 end_early;		// the next pass looks different: end the block before it
 	u32 failed;
 	u32 obit_lo, obit_hi;	// output bit position (64-bit)
 	u32 pre_lens_packed[3];
@@ -612,6 +611,49 @@ __device__ void lz_dp_segment(const u8 *ring, const u32 *mlist, u32 *costg, u32 
 	__syncwarp();
 }
 
+// ---- block splitting (ref: observe_literal / do_end_block_check, lib/deflate_compress.c:2105-2190) ---
+// The reference watches 8 literal classes (top 2 bits + low bit of the byte) and ends a block when
+// the distribution of the newest observations differs from the block so far by >= 200/512 in L1.
+// Here blocks end on pass boundaries, so the test runs once per pass, on the bytes of the pass that
+// would join the block: lz_observe() counts their classes (all threads), lz_should_end_block()
+// applies the reference's integer arithmetic to the two histograms.
+__device__ __forceinline__ void lz_observe(const u8 *ring, u32 from, u32 to, u32 *obs, u32 tid, u32 lane)
+{
+	// 16 bytes per thread and round; class counts in 8 packed byte fields, reduced per warp
+	for (u32 wbase = from + 512 * (tid >> 5); wbase < to; wbase += 16 * LZ_THREADS) {	// warp-uniform trip count
+		const u32 base = wbase + 16 * lane;
+		const uint4 q = *(const uint4 *)(ring + (base & (LZ_RING - 1)));	// from is 16 KiB aligned
+		const u32 w[4] = {q.x, q.y, q.z, q.w};
+		u64 cnt = 0;
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			const u32 bv = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
+			if (base + k < to) cnt += (u64)1 << (8 * (((bv >> 5) & 6) | (bv & 1)));
+		}
+		u64 lo = cnt & 0x00ff00ff00ff00ffull, hi = (cnt >> 8) & 0x00ff00ff00ff00ffull;	// classes 0,2,4,6 / 1,3,5,7
+		for (int o = 16; o > 0; o >>= 1) {
+			lo += __shfl_xor_sync(LDB_FULL_MASK, lo, o);
+			hi += __shfl_xor_sync(LDB_FULL_MASK, hi, o);
+		}
+		if (lane < 4) atomicAdd(&obs[2 * lane], (u32)(lo >> (16 * lane)) & 0xffff);
+		else if (lane < 8) atomicAdd(&obs[2 * (lane - 4) + 1], (u32)(hi >> (16 * (lane - 4))) & 0xffff);
+	}
+}
+
+__device__ __forceinline__ bool lz_should_end_block(const u32 *obs, const u32 *obs_new, u32 block_length)
+{
+	u32 n_old = 0, n_new = 0;
+	for (int i = 0; i < 8; i++) { n_old += obs[i]; n_new += obs_new[i]; }
+	if (!n_old || !n_new) return false;
+	u64 total_delta = 0;
+	for (int i = 0; i < 8; i++) {
+		const u64 expected = (u64)obs[i] * n_new, actual = (u64)obs_new[i] * n_old;
+		total_delta += actual > expected ? actual - expected : expected - actual;
+	}
+	const u64 cutoff = (u64)n_new * 200 / 512 * n_old;
+	return total_delta + (u64)(block_length / 4096) * n_old >= cutoff;
+}
+
 // ---- the kernel ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 ldb_deflate_lz_kernel(ldb_deflate_args a)
@@ -737,28 +779,28 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 		auto parse_pass = [&](const u32 pb0, const u32 ppend, const u32 aoff, const bool forced) {
 			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
 			const u32 nwin = (ppend - pb0 + 31) >> 5;
-			// (the loads of the next window are issued before the current one is processed)
+			// (the per-position results live in L2: the loads run two windows ahead of their use)
 			const u32 min_len = v->min_len;
-			u32 nW0 = 0, nW1 = 0, nW2 = 0;
-			if (warp < nwin) {
-				u32 i = warp * 32 + lane;
-				if (pb0 + i < ppend) nW0 = res[aoff + i];
-				if (lane == 31 && pb0 + i + 1 < ppend) nW1 = res[aoff + i + 1];	// (the others get it by shuffle)
-				if (lane == 31 && P.lazy == 2 && pb0 + i + 2 < ppend) nW2 = res[aoff + i + 2];
-			}
+			auto e1_load = [&](u32 w, u32 &x0, u32 &x1, u32 &x2) {
+				x0 = 0; x1 = 0; x2 = 0;
+				if (w < nwin) {
+					const u32 i = w * 32 + lane;
+					if (pb0 + i < ppend) x0 = res[aoff + i];
+					if (lane == 31 && pb0 + i + 1 < ppend) x1 = res[aoff + i + 1];	// (the others get it by shuffle)
+					if (lane == 31 && P.lazy == 2 && pb0 + i + 2 < ppend) x2 = res[aoff + i + 2];
+				}
+			};
+			u32 cW0, cW1, cW2, nW0, nW1, nW2;
+			e1_load(warp, cW0, cW1, cW2);
+			e1_load(warp + LZ_WARPS, nW0, nW1, nW2);
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				u32 i = w * 32 + lane;
 				u32 p = pb0 + i;
-				const u32 W0 = nW0, nb = __shfl_down_sync(LDB_FULL_MASK, W0, 1), W1 = lane == 31 ? nW1 : nb;
-				const u32 nb2 = __shfl_down_sync(LDB_FULL_MASK, W1, 1), W2 = lane == 31 ? nW2 : nb2;	// two ahead (lazy2)
+				const u32 W0 = cW0, nb = __shfl_down_sync(LDB_FULL_MASK, W0, 1), W1 = lane == 31 ? cW1 : nb;
+				const u32 nb2 = __shfl_down_sync(LDB_FULL_MASK, W1, 1), W2 = lane == 31 ? cW2 : nb2;	// two ahead (lazy2)
 				const u32 L0 = W0 & 0xffff, O0 = ((W0 >> 16) & 0x7fff) + 1, L1 = W1 & 0xffff, O1 = ((W1 >> 16) & 0x7fff) + 1;
-				if (w + LZ_WARPS < nwin) {
-					u32 i2 = i + LZ_WARPS * 32;
-					nW0 = 0; nW1 = 0; nW2 = 0;
-					if (pb0 + i2 < ppend) nW0 = res[aoff + i2];
-					if (lane == 31 && pb0 + i2 + 1 < ppend) nW1 = res[aoff + i2 + 1];
-					if (lane == 31 && P.lazy == 2 && pb0 + i2 + 2 < ppend) nW2 = res[aoff + i2 + 2];
-				}
+				cW0 = nW0; cW1 = nW1; cW2 = nW2;
+				e1_load(w + 2 * LZ_WARPS, nW0, nW1, nW2);
 				bool is_match = forced ? ((L0 >= 3) && p < ppend) : (L0 >= min_len && p < ppend);
 				if (!forced && is_match && P.lazy && p + 1 < ppend) {
 					// ref: deflate_compress.c:2722-2725 -- prefer the next position's match if clearly better
@@ -873,20 +915,21 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			__syncthreads();
 			LZ_T(9);
 			// (e3) visited sets per window (the loads of the next window are issued first)
-			u32 e3_e = 0xff, e3_w = 0;
-			if (warp < nwin) {
-				const u32 i = warp * 32 + lane;
-				e3_e = entryt[warp];
-				if (e3_e != 0xff && pb0 + i < ppend) e3_w = res[aoff + i];
-			}
+			auto e3_load = [&](u32 w, u32 &e, u32 &x) {
+				e = 0xff; x = 0;
+				if (w < nwin) {
+					const u32 i = w * 32 + lane;
+					e = entryt[w];
+					if (e != 0xff && pb0 + i < ppend) x = res[aoff + i];
+				}
+			};
+			u32 e3_e, e3_w, e3_ne, e3_nw;
+			e3_load(warp, e3_e, e3_w);
+			e3_load(warp + LZ_WARPS, e3_ne, e3_nw);
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				const u32 e = e3_e, rw = e3_w;
-				if (w + LZ_WARPS < nwin) {
-					const u32 i2 = (w + LZ_WARPS) * 32 + lane;
-					e3_e = entryt[w + LZ_WARPS];
-					e3_w = 0;
-					if (e3_e != 0xff && pb0 + i2 < ppend) e3_w = res[aoff + i2];
-				}
+				e3_e = e3_ne; e3_w = e3_nw;
+				e3_load(w + 2 * LZ_WARPS, e3_ne, e3_nw);
 				u32 V = 0;
 				if (e != 0xff) {
 					u32 step = (rw & 0x80000000u) ? (rw & 0xffff) : 1;
@@ -932,20 +975,21 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			LZ_T(11);
 			// (e5) emit tokens + histograms
 			const u32 tbase = v->tok_count;
-			u32 e5_V = 0, e5_w = 0;
-			if (warp < nwin) {
-				const u32 i = warp * 32 + lane;
-				e5_V = vis[warp];
-				if ((e5_V >> lane) & 1) e5_w = res[aoff + i];
-			}
+			auto e5_load = [&](u32 w, u32 &V, u32 &x) {
+				V = 0; x = 0;
+				if (w < nwin) {
+					V = vis[w];
+					if ((V >> lane) & 1) x = res[aoff + w * 32 + lane];
+				}
+			};
+			u32 e5_V, e5_w, e5_nV, e5_nw;
+			e5_load(warp, e5_V, e5_w);
+			e5_load(warp + LZ_WARPS, e5_nV, e5_nw);
 			for (u32 w = warp; w < nwin; w += LZ_WARPS) {
 				const u32 V = e5_V, ro = e5_w >> 16;
 				const u32 len = e5_w & 0xffff;
-				if (w + LZ_WARPS < nwin) {
-					const u32 i2 = (w + LZ_WARPS) * 32 + lane;
-					e5_V = vis[w + LZ_WARPS];
-					if ((e5_V >> lane) & 1) e5_w = res[aoff + i2];
-				}
+				e5_V = e5_nV; e5_w = e5_nw;
+				e5_load(w + 2 * LZ_WARPS, e5_nV, e5_nw);
 				if (!V) continue;
 				u32 i = w * 32 + lane;
 				if ((V >> lane) & 1) {
@@ -1111,8 +1155,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			if (b0 == 0) {
 				// alphabet size of the first 4 KiB -> minimum match length (ref:
 				// calculate_min_match_len, lib/deflate_compress.c:2329-2346)
-				if (tid < 8) v->used_lits[tid] = 0;
+				if (tid < 8) { v->used_lits[tid] = 0; v->obs_blk[tid] = 0; }
 				__syncthreads();
+				lz_observe(ring, 0, pend, v->obs_blk, tid, lane);
 				const u32 scan = n < 4096 ? n : 4096;
 				for (u32 i = tid; i < scan; i += LZ_THREADS) {
 					u32 bv = ring[i];
@@ -1160,35 +1205,20 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// A run starts its walk without knowing where the parse really enters it, so short
 				// runs cost a little ratio (L6: +0.9 % at 16 vs 32) and buy parallelism; the deep
 				// levels, which are chosen for ratio, keep 32.
-				const u32 run_len = (a.level >= 7 || LZ_PASS / 16 > LZ_THREADS) ? 32 : 16;
-				// A run takes between ~2 trips of the loop below (long matches) and run_len trips (all
-				// literals), one search per trip.  To keep the lanes of a warp alive together, a thread
-				// works on a run for at most LZ_TRIPS trips per round; unfinished runs are queued with
-				// their (tiny) walk state and dealt out again, densely packed, in the next round.  Who
-				// continues a run does not matter, so the result is deterministic.
-				const u32 nruns = (pend - b0 + run_len - 1) / run_len;
-				u32 *qlist = (u32 *)(sm + LZ_SM_R);		// 2 words per queued run (<= 8 KiB)
-				u32 nitems = nruns;
-				for (u32 round = 0; nitems; round++) {
+				const u32 run_len = a.level >= 7 ? 32 : 16;
+				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
+				// (long matches, few searches) take more of them, which keeps the warp busy
 				u32 i = 0, i_end = 0;
 				u32 pL = 0, pD = 0;		// pending match at position i-pending (lazy evaluation in progress)
 				u32 pending = 0;		// 0: none, 1: looking one position ahead, 2: two positions (lazy2)
-				const bool have = tid < nitems;
-				if (have) {
-					if (round == 0) {
-						i = tid * run_len;
-						i_end = i + run_len < pend - b0 ? i + run_len : pend - b0;
-					} else {
-						const u32 q0 = qlist[2 * tid], q1 = qlist[2 * tid + 1];
-						i = q0 & 0xffff; i_end = q0 >> 16;
-						pending = q1 >> 30; pL = (q1 >> 15) & 0x1ff; pD = q1 & 0x7fff;
+				for (;;) {
+					if (i >= i_end || b0 + i >= pend) {
+						const u32 r = atomicAdd(&v->run_counter, 1u);
+						i = r * run_len;
+						if (b0 + i >= pend || i >= LZ_PASS) break;
+						i_end = i + run_len;
+						pending = 0;
 					}
-				}
-				__syncthreads();
-				if (tid == 0) v->run_counter = 0;	// tail of the queue being filled
-				__syncthreads();
-				if (have) {
-				for (u32 trip = 0; trip < LZ_TRIPS && i < i_end; trip++) {
 					const u32 p = b0 + i;
 					u32 L = 0, D = 0;
 					if (p + 4 <= n) {
@@ -1243,15 +1273,6 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						i++;
 					}
 				}
-				if (i < i_end) {
-					const u32 k = atomicAdd(&v->run_counter, 1u);
-					qlist[2 * k] = i | (i_end << 16);
-					qlist[2 * k + 1] = (pending << 30) | (pL << 15) | pD;
-				}
-				}	// have
-				__syncthreads();
-				nitems = v->run_counter;
-				}	// rounds
 				}	// guided search (levels 1-9)
 			}
 			__syncthreads();
@@ -1260,8 +1281,21 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			parse_pass(b0, pend, pass_in_block * LZ_PASS, false);
 			LZ_T(2);	// parse
 			// ---- block boundary: every LZ_BLOCK_PASSES passes, or at the end of the input --------
+			// A block also ends early when the bytes of the next pass look different from the block
+			// so far (the reference's block-split test, on pass granularity).
 			pass_in_block++;
-			if (!(last || pass_in_block == LZ_BLOCK_PASSES)) continue;
+			if (!last) {
+				if (tid < 8) v->obs_next[tid] = 0;
+				__syncthreads();
+				lz_observe(ring, pend, pend + LZ_PASS < n ? pend + LZ_PASS : n, v->obs_next, tid, lane);
+				__syncthreads();
+				if (tid == 0) v->end_early = lz_should_end_block(v->obs_blk, v->obs_next, pend - block_begin) ? 1 : 0;
+				__syncthreads();
+				const bool end_now = pass_in_block == LZ_BLOCK_PASSES || v->end_early;
+				__syncthreads();
+				if (tid < 8) v->obs_blk[tid] = end_now ? v->obs_next[tid] : v->obs_blk[tid] + v->obs_next[tid];
+				if (!end_now) continue;
+			}
 			const u32 npass_block = pass_in_block;
 			pass_in_block = 0;
 			const u32 block_end = pend;

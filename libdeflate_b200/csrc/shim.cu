@@ -472,7 +472,7 @@ struct host_span {
 	bool compact;
 };
 
-// If the host chunks sit (nearly) back to back in one allocation, the whole span is
+// If the host chunks sit back to back or in regular slots of one allocation, the whole span is
 // moved with a single copy and device pointers are base + (h_ptr - lo).  For output
 // buffers the span is copied BACK over host memory, so 'exact' demands that the
 // buffers tile the span with no gaps at all (nothing that is not the caller's
@@ -491,7 +491,9 @@ static host_span span_of(const void *const *ptrs, const size_t *sizes, size_t n,
 	}
 	if (s.lo) {
 		if (exact) s.compact = tiled && (size_t)(s.hi - s.lo) == s.sum;
-		else s.compact = (size_t)(s.hi - s.lo) <= s.sum + (s.sum >> 2) + 64 * n + 4096;
+		// inputs: gaps are simply transferred too as long as the span stays within 4x the payload
+		// (e.g. streams sitting in compress_bound()-sized slots); one DMA beats n small ones
+		else s.compact = (size_t)(s.hi - s.lo) <= 4 * s.sum + 64 * n + 4096;
 	}
 	return s;
 }
