@@ -13,11 +13,8 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    "trips2": ["-DLZ_TRIPS=2"],
-    "trips4": ["-DLZ_TRIPS=4"],
-    "trips8": ["-DLZ_TRIPS=8"],
-    "trips32": ["-DLZ_TRIPS=32"],
-    "trips4tim": ["-DLZ_TRIPS=4", "-DLZ_TIMING"],
+    "dbl": [],
+    "dbltim": ["-DLZ_TIMING"],
 }
 
 

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in trips2 trips4 trips8 trips32 trips4tim; do
+for v in prev dbl prev dbl dbltim; do
   echo "== $v"
   timeout 300 python scripts/variant_bench.py $v roundtrip 16384 2> gpurun_out/var_$v.err | python -c "
 import sys, json
