@@ -1532,7 +1532,11 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			}
 			__syncthreads();
 			const u32 cost_dyn = v->cost_dyn, cost_static = v->cost_static;
-			const u32 blen = block_end - block_begin;
+			// The tokens of this block cover [block_entry, parse_entry): its first token starts where the
+			// previous block's last match ended and its own last match may run past block_end.  A
+			// stored block must cover exactly the same bytes.
+			// (past the end of the input the parser's continuation point is only window-granular)
+			const u32 sbeg = block_entry, blen = (v->parse_entry < n ? v->parse_entry : n) - block_entry;
 			const u32 bitoff = (u32)(o.obit & 7);
 			const u32 stored_pieces = blen ? (blen + 65534) / 65535 : 1;
 			// first piece: 3 header bits + pad to a byte; later pieces start byte aligned
@@ -1559,9 +1563,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			__syncthreads();
 			if (btype == DEFLATE_BLOCKTYPE_STORED) {
 				// ---- stored: header bits via staging, raw bytes straight from the input
-				u32 src = block_begin;
+				u32 src = sbeg;
 				for (u32 piece = 0; piece < stored_pieces; piece++) {
-					u32 len = blen - (src - block_begin) > 65535 ? 65535 : blen - (src - block_begin);
+					u32 len = blen - (src - sbeg) > 65535 ? 65535 : blen - (src - sbeg);
 					bool fin = last && piece + 1 == stored_pieces;
 					if (tid == 0) {
 						lz_stage_or(stage, (u32)(o.obit - (w0 << 5)), fin ? 1 : 0, 3);

@@ -185,3 +185,29 @@ def check_host_pipeline(library, ctx, n=2304, chunk=4096):
                                                        oav.ctypes.data, None, aout.ctypes.data, res.ctypes.data, n)
     assert rc == 0 and (res == 0).all() and (aout == chunk).all()
     assert out.tobytes() == raw
+
+
+def boundary_chunks():
+    """Inputs whose compressible/incompressible seams sit a few bytes off the compressor's 16 KiB pass and
+    32 KiB block boundaries: a match that runs across a block end next to a block that is emitted stored
+    (regression: the stored block must cover exactly the bytes its tokens would have covered)."""
+    import corpus
+    out = []
+    k = 0
+    for seam in (16384, 32768, 49152, 65536, 98304):
+        for d in (-9, -1, 0, 1, 8, 100, 257):
+            k += 1
+            a = seam + d
+            out.append(corpus.text(a, k) + corpus.rand(40000 - (k % 3) * 7001, k))
+            out.append(corpus.rand(a, k) + corpus.text(33000 + k, k) + corpus.rand(17000, k + 1))
+    return out
+
+
+def check_boundary_round_trip(ctx, levels=(1, 6, 9, 12), fmt=0, every=1):
+    chunks = boundary_chunks()[::every]
+    wbits = {0: -15, 1: 15, 2: 31}[fmt]
+    for lvl in levels:
+        zs = ctx.compress_batch_host(chunks, lvl, fmt)
+        for c, z in zip(chunks, zs):
+            assert z is not None, ("did not fit its bound", lvl, len(c))
+            assert zlib.decompress(z, wbits) == c, ("round trip", lvl, len(c))

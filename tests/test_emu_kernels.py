@@ -32,6 +32,10 @@ def test_deflate_round_trip_emulated(emu_ctx, oracle, reflib):
     pc.check_compress_round_trip(emu_ctx, oracle, chunks[:6], levels=(3, 9), fmts=(1,))
 
 
+def test_deflate_stored_blocks_next_to_crossing_matches_emulated(emu_ctx):
+    pc.check_boundary_round_trip(emu_ctx, levels=(1, 6), every=6)	# (the full sweep runs on the GPU)
+
+
 def test_inflate_output_primitives_unit():
     """Randomized unit test of the word-accumulator / match-copy primitives (host build)."""
     import os
