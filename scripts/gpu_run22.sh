@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in inf_a inf_ob6s8 inf_ob6s16 inf_ldcg inf_a; do
+for v in inf_w15 inf_w13 inf_w12 inf_w11 inf_w9; do
   echo "== $v"
   timeout 300 python scripts/variant_bench.py $v decompress 65536 2> gpurun_out/var_$v.err | python -c "
 import sys, json
