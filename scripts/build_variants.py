@@ -13,11 +13,7 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    "inf_w15": [],
-    "inf_w13": ["-DINF_WPC=13"],
-    "inf_w12": ["-DINF_WPC=12"],
-    "inf_w11": ["-DINF_WPC=11"],
-    "inf_w9": ["-DINF_WPC=9"],
+    "tim": ["-DLZ_TIMING"],
 }
 
 

@@ -116,6 +116,10 @@ def test_compress_batch_round_trip_and_bound(gpu_ctx, oracle):
                 assert r[0] == 0 and r[1] == c, (fmt, lvl, len(c))
 
 
+def test_compress_stored_blocks_next_to_crossing_matches(gpu_ctx):
+    pc.check_boundary_round_trip(gpu_ctx, levels=(1, 4, 6, 9, 10, 12), fmt=2)
+
+
 def test_pipelined_host_path(gpu_ctx):
     import libdeflate_b200 as ldb
     pc.check_host_pipeline(ldb.lib(), gpu_ctx, n=8192, chunk=65536)
