@@ -311,7 +311,9 @@ __device__ __forceinline__ void lz_gen_codes_serial(const u8 *lens, u32 nsyms, u
 
 #ifdef LZ_TIMING
 #include <stdio.h>
-// tuning builds only: cycles per phase, summed over all CTAs (thread 0's clock between barriers)
+// tuning builds only: cycles per phase, summed over all CTAs (thread 0's clock between barriers;
+// the compiler may read the clock before the barrier wait, so a phase in which thread 0 finishes early
+// is under-counted and the wait shows up in the next one: read 'search phase' + 'parse e1' together)
 __device__ unsigned long long ldb_lz_timing[16];
 #define LZ_T(k) do { if (tid == 0) { long long t_ = clock64(); tacc[k] += t_ - tlast; tlast = t_; } } while (0)
 #else
@@ -684,7 +686,6 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 	// per-position results of the current pass live in this CTA's global scratch
 	u8 *gs = a.scratch + (size_t)blockIdx.x * LZ_GS_BYTES;
 	u32 *res = (u32 *)(gs + LZ_GS_RES);	// per position: match length | (distance-1 | decision flag << 15) << 16
-	u16 *exitt = (u16 *)(gs + LZ_GS_EXIT);
 	u32 *tokbuf = (u32 *)(gs + LZ_GS_TOK);
 	u32 *costg = (u32 *)(gs + LZ_GS_COST);
 	u32 *mlist = (u32 *)(gs + LZ_GS_MLIST);
@@ -776,7 +777,9 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 
 		// ---- exact parallel parse of one pass (positions [pb0, ppend), results at res[aoff + i]).
 		// forced: the DP already decided (flag set on matches); otherwise the lazy rule decides.
-		auto parse_pass = [&](const u32 pb0, const u32 ppend, const u32 aoff, const bool forced) {
+		// exitt: 16 Ki u16 of scratch in shared memory -- the link slots of the first pass that is not
+		// inserted yet (dead, see lz_insert_pass_par)
+		auto parse_pass = [&](const u32 pb0, const u32 ppend, const u32 aoff, const bool forced, u16 *exitt) {
 			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
 			const u32 nwin = (ppend - pb0 + 31) >> 5;
 			// (the per-position results live in L2: the loads run two windows ahead of their use)
@@ -1278,7 +1281,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			__syncthreads();
 			LZ_T(1);	// search phase (barrier to barrier)
 			// (e) exact parallel parse of this pass -> tokens + histograms
-			parse_pass(b0, pend, pass_in_block * LZ_PASS, false);
+			parse_pass(b0, pend, pass_in_block * LZ_PASS, false, nextt + ((b0 + LZ_PASS) & 0xffff));
 			LZ_T(2);	// parse
 			// ---- block boundary: every LZ_BLOCK_PASSES passes, or at the end of the input --------
 			// A block also ends early when the bytes of the next pass look different from the block
@@ -1342,7 +1345,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				for (u32 pp = 0; pp < npass_block; pp++) {
 					u32 pb0 = block_begin + pp * LZ_PASS;
 					u32 ppend = pb0 + LZ_PASS < block_end ? pb0 + LZ_PASS : block_end;
-					parse_pass(pb0, ppend, pp * LZ_PASS, true);
+					parse_pass(pb0, ppend, pp * LZ_PASS, true, nextt + ((block_begin + npass_block * LZ_PASS) & 0xffff));
 				}
 			}
 			const u32 ntok = v->tok_count;

@@ -12,3 +12,15 @@ for line in sys.stdin:
         print(line)
 "
 done
+for v in prev exsm prev exsm; do
+  echo "== $v"
+  timeout 300 python scripts/variant_bench.py $v roundtrip 16384 2> gpurun_out/var_$v.err | python -c "
+import sys, json
+for line in sys.stdin:
+    line = line.rstrip()
+    if line.startswith('{'):
+        d = json.loads(line); print(d['value'], d['kernel_ms_per_step'])
+    else:
+        print(line)
+"
+done
