@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in inf_w15 inf_w13 inf_w12 inf_w11 inf_w9; do
+for v in i_base i_r3 i_r6 i_m4 i_m16 i_c8 i_r6m16 i_base; do
   echo "== $v"
   timeout 300 python scripts/variant_bench.py $v decompress 65536 2> gpurun_out/var_$v.err | python -c "
 import sys, json
