@@ -83,8 +83,7 @@
 #define LZ_OPT_K     8					// matches kept per position (levels 10-12)
 #define LZ_DP_SEG    2048				// positions per independent DP segment (one warp each)
 #define LZ_GS_RES    0						// u32[BLOCK_POS]  block-relative
-#define LZ_GS_EXIT   (LZ_GS_RES + 4 * LZ_BLOCK_POS)		// u16[PASS]       pass-relative
-#define LZ_GS_TOK    (LZ_GS_EXIT + 2 * LZ_PASS)			// u32[TOKCAP]
+#define LZ_GS_TOK    (LZ_GS_RES + 4 * LZ_BLOCK_POS)		// u32[TOKCAP]
 #define LZ_GS_COST   (LZ_GS_TOK + 4 * LZ_TOKCAP)		// u32[BLOCK_POS + 320]   (levels 10-12)
 #define LZ_GS_MLIST  (LZ_GS_COST + 4 * (LZ_BLOCK_POS + 320))	// u32[BLOCK_POS * K]     (levels 10-12)
 #define LZ_GS_BYTES  (LZ_GS_MLIST + 4 * LZ_BLOCK_POS * LZ_OPT_K)
