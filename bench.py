@@ -275,7 +275,19 @@ def run_b200(args):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout when the first communicator comes up; the contract is ONE
+        # JSON line on stdout, so stdout points at stderr until that has happened
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         dist = dist_mod
     red = shard.Reducer(dist, "cuda" if dist else "cpu")
     barrier, allmax, allsum = red.barrier, red.max, red.sum
