@@ -87,6 +87,7 @@
 #define LZ_GS_COST   (LZ_GS_TOK + 4 * LZ_TOKCAP)		// u32[BLOCK_POS + 320]   (levels 10-12)
 #define LZ_GS_MLIST  (LZ_GS_COST + 4 * (LZ_BLOCK_POS + 320))	// u32[BLOCK_POS * K]     (levels 10-12)
 #define LZ_GS_BYTES  (LZ_GS_MLIST + 4 * LZ_BLOCK_POS * LZ_OPT_K)
+#define LZ_FAR4_DIST  1024				// text-like input: a 4-byte match further away than this is coded as literals
 #define LZ_COST_INF  0x3fffffu				// fits the 23-bit cost field of the DP reduction key
 
 struct lz_vars {
@@ -99,6 +100,7 @@ struct lz_vars {
 	u32 n_items;
 	u32 run_counter;	// next unassigned search run of the current pass
 	u32 min_len;		// shortest match worth taking (depends on the alphabet size)
+	u32 far4_dist;		// 4-byte matches further away than this are coded as literals
 	u32 used_lits[8];	// 256-bit set of byte values seen in the first 4 KiB
 	u32 carry;		// partial output word at bit position obit (persists between flushes)
 	u32 nused_lit, nused_off;
@@ -782,7 +784,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 			// (e1) per-window decisions + "exit position for every entry lane" by pointer jumping
 			const u32 nwin = (ppend - pb0 + 31) >> 5;
 			// (the per-position results live in L2: the loads run two windows ahead of their use)
-			const u32 min_len = v->min_len;
+			const u32 min_len = v->min_len, far4 = v->far4_dist;
 			auto e1_load = [&](u32 w, u32 &x0, u32 &x1, u32 &x2) {
 				x0 = 0; x1 = 0; x2 = 0;
 				if (w < nwin) {
@@ -803,7 +805,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				const u32 L0 = W0 & 0xffff, O0 = ((W0 >> 16) & 0x7fff) + 1, L1 = W1 & 0xffff, O1 = ((W1 >> 16) & 0x7fff) + 1;
 				cW0 = nW0; cW1 = nW1; cW2 = nW2;
 				e1_load(w + 2 * LZ_WARPS, nW0, nW1, nW2);
-				bool is_match = forced ? ((L0 >= 3) && p < ppend) : (L0 >= min_len && p < ppend);
+				// (a shortest-possible match at a long distance costs more bits than its literals: the
+				// reference's rule for length 3 beyond 8 KiB, deflate_compress.c:2666-2668, restated for our
+				// minimum length 4)
+				bool is_match = forced ? ((L0 >= 3) && p < ppend) : (L0 >= min_len && p < ppend && !(L0 == 4 && O0 > far4));
 				if (!forced && is_match && P.lazy && p + 1 < ppend) {
 					// ref: deflate_compress.c:2722-2725 -- prefer the next position's match if clearly better
 					if (L1 >= L0 && L0 < (u32)P.nice &&
@@ -1170,6 +1175,8 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					u32 cnt = 0;
 					for (int k = 0; k < 8; k++) cnt += __popc(v->used_lits[k]);
 					v->min_len = n < 512 ? 4 : lz_choose_min_len(cnt, (u32)P.depth);
+					// few distinct byte values = cheap literals (text): a far 4-byte match loses against them
+					v->far4_dist = cnt < 80 ? LZ_FAR4_DIST : LZ_WIN;
 				}
 				__syncthreads();
 			}
@@ -1203,7 +1210,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 						rs[i] = L ? L | ((D - 1) << 16) : 0;
 					}
 				} else {
-				const u32 min_len = v->min_len;
+				const u32 min_len = v->min_len, far4 = v->far4_dist;
 				// A run starts its walk without knowing where the parse really enters it, so short
 				// runs cost a little ratio (L6: +0.9 % at 16 vs 32) and buy parallelism; the deep
 				// levels, which are chosen for ratio, keep 32.
@@ -1245,7 +1252,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 							mpos = i - pending; mL = pL; mD = pD;
 							pending = 0;
 						}
-					} else if (L >= min_len) {
+					} else if (L >= min_len && !(L == 4 && D > far4)) {
 						if (P.lazy && L < (u32)P.nice && i + 1 < i_end && b0 + i + 1 < pend) {
 							pending = 1; pL = L; pD = D;
 							mpos = i; mL = 0; mD = 0;
