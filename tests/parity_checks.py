@@ -211,3 +211,32 @@ def check_boundary_round_trip(ctx, levels=(1, 6, 9, 12), fmt=0, every=1):
         for c, z in zip(chunks, zs):
             assert z is not None, ("did not fit its bound", lvl, len(c))
             assert zlib.decompress(z, wbits) == c, ("round trip", lvl, len(c))
+
+
+def check_random_mix_round_trip(ctx, seed=1, rounds=3, per_round=8):
+    """Randomised sizes / content mixes / levels / formats: compress, inflate with zlib AND with our own
+    decompressor.  (The seam cases above were found with this kind of sweep.)"""
+    import random
+    import corpus
+    rng = random.Random(seed)
+    gens = [corpus.text, corpus.rand, lambda n, s: corpus.zeros(n), lambda n, s: corpus.pattern(n), corpus.mixed]
+    for _ in range(rounds):
+        chunks = []
+        for _k in range(per_round):
+            total = rng.choice([0, 1, 7, 100, 3000, 16384, 20000, 32768, 40000, 65536, 70000, 100000])
+            total = max(0, total + rng.randint(-40, 40)) if total > 50 else total
+            parts, left = [], total
+            while left > 0:
+                n = min(left, rng.choice([5, 50, 500, 4000, 16000, 16384, 33000, 70000]))
+                parts.append(rng.choice(gens)(n, rng.randint(0, 10 ** 6))[:n])
+                left -= n
+            chunks.append(b"".join(parts))
+        lvl = rng.choice(range(13))
+        fmt = rng.choice([0, 1, 2])
+        wbits = {0: -15, 1: 15, 2: 31}[fmt]
+        zs = ctx.compress_batch_host(chunks, lvl, fmt)
+        for c, z in zip(chunks, zs):
+            assert z is not None and zlib.decompress(z, wbits) == c, ("round trip", lvl, fmt, len(c))
+        outs = ctx.decompress_batch_host(zs, [len(c) for c in chunks], fmt)
+        for c, o in zip(chunks, outs):
+            assert o[0] == 0 and o[1] == c, ("own inflate", lvl, fmt, len(c))

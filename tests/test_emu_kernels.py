@@ -37,6 +37,10 @@ def test_deflate_stored_blocks_next_to_crossing_matches_emulated(emu_ctx):
     pc.check_boundary_round_trip(emu_ctx, levels=(1, 6), every=6)	# (the full sweep runs on the GPU)
 
 
+def test_deflate_random_mix_emulated(emu_ctx):
+    pc.check_random_mix_round_trip(emu_ctx, seed=3, rounds=3)
+
+
 def test_inflate_output_primitives_unit():
     """Randomized unit test of the word-accumulator / match-copy primitives (host build)."""
     import os

@@ -120,6 +120,10 @@ def test_compress_stored_blocks_next_to_crossing_matches(gpu_ctx):
     pc.check_boundary_round_trip(gpu_ctx, levels=(1, 4, 6, 9, 10, 12), fmt=2)
 
 
+def test_compress_random_mix(gpu_ctx):
+    pc.check_random_mix_round_trip(gpu_ctx, seed=7, rounds=12, per_round=24)
+
+
 def test_pipelined_host_path(gpu_ctx):
     import libdeflate_b200 as ldb
     pc.check_host_pipeline(ldb.lib(), gpu_ctx, n=8192, chunk=65536)
