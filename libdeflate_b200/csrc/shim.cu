@@ -504,7 +504,16 @@ struct staged_batch {
 	u8 *d_base;		// device slab
 	std::size_t slab_bytes;
 	bool compact;
-	size_t *offsets;	// host, per chunk offset into slab (malloc'd)
+	size_t *offsets;	// host, per chunk offset into slab (malloc'd, owned)
+	~staged_batch() { free(offsets); }
+};
+// host scratch that is released on every exit path (the CUDA error checks return early)
+struct host_scratch {
+	void *p;
+	explicit host_scratch(size_t n) : p(malloc(n)) {}
+	~host_scratch() { free(p); }
+	host_scratch(const host_scratch &) = delete;
+	host_scratch &operator=(const host_scratch &) = delete;
 };
 
 // Lays out n buffers of the given sizes in a device slab (16-byte aligned each, or
@@ -585,9 +594,11 @@ static bool pipeline_eligible(const libdeflate_b200_ctx *ctx, const void *const 
 	return a.compact && b.compact && host_ordered(h_in, in_sz, n) && host_ordered(h_out, out_sz, n);
 }
 
+static void pipe_events_destroy(struct pipe_events *e);
 struct pipe_events {
 	cudaEvent_t in[LDB_PIPE_MAX_STAGES], done[LDB_PIPE_MAX_STAGES];
-	int n;
+	int n = 0;
+	~pipe_events() { pipe_events_destroy(this); }
 };
 static int pipe_events_create(pipe_events *e, int n)
 {
@@ -602,6 +613,7 @@ static int pipe_events_create(pipe_events *e, int n)
 static void pipe_events_destroy(pipe_events *e)
 {
 	for (int i = 0; i < e->n; i++) { cudaEventDestroy(e->in[i]); cudaEventDestroy(e->done[i]); }
+	e->n = 0;
 }
 // min_chunks: smallest sub-batch that still fills the kernel of this direction (the inflate kernel
 // decodes one chunk per lane, ~71 K lanes resident; the deflate kernel one chunk per CTA)
@@ -629,7 +641,8 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 	size_t res_bytes = 2 * align_up(n * sizeof(size_t), 256) + align_up(n * sizeof(s32), 256);
 	int rc = ldb_reserve_dev(ctx->d_params, res_off + res_bytes);
 	if (rc) return rc;
-	u8 *hparam = (u8 *)malloc(res_off + res_bytes);
+	host_scratch hparam_own(res_off + res_bytes);
+	u8 *hparam = (u8 *)hparam_own.p;
 	if (!hparam) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
 	u8 *dparam = (u8 *)ctx->d_params.p;
 	const bool pipelined = pipeline_eligible(ctx, h_in, h_in_nbytes, (const void *const *)h_out, h_out_avail, n);
@@ -700,9 +713,6 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 			if (h_actual_out) h_actual_out[i] = r_aout[i];
 		}
 	}
-	free(in_sb.offsets);
-	free(out_sb.offsets);
-	free(hparam);
 	return rc;
 }
 
@@ -718,7 +728,8 @@ extern "C" int libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *c
 	size_t res_bytes = align_up(n * sizeof(size_t), 256);
 	int rc = ldb_reserve_dev(ctx->d_params, res_off + res_bytes);
 	if (rc) return rc;
-	u8 *hparam = (u8 *)malloc(res_off + res_bytes);
+	host_scratch hparam_own(res_off + res_bytes);
+	u8 *hparam = (u8 *)hparam_own.p;
 	if (!hparam) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
 	u8 *dparam = (u8 *)ctx->d_params.p;
 	const bool pipelined = pipeline_eligible(ctx, h_in, h_in_nbytes, (const void *const *)h_out, h_out_avail, n);
@@ -777,9 +788,6 @@ extern "C" int libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *c
 		if (!rc) rc = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
 		for (size_t i = 0; i < n; i++) h_out_nbytes[i] = r_on[i];
 	}
-	free(in_sb.offsets);
-	free(out_sb.offsets);
-	free(hparam);
 	return rc;
 }
 
