@@ -149,6 +149,36 @@ libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *ctx, int format,
 				    void *const *h_out, const size_t *h_out_avail,
 				    size_t *h_out_nbytes, size_t n_chunks);
 
+/*
+ * One large buffer <-> a blocked gzip file (BGZF: RFC 1952 members of at most
+ * 65280 input bytes, each carrying its own size in a "BC" extra subfield, plus the
+ * 28-byte empty end-of-file member) -- the pigz / bgzip way of making ONE file
+ * data-parallel.  Any gunzip reads the result (it is a multi-member gzip file);
+ * the decompressor here needs the BC subfields to find the members without
+ * decoding (ref for the caller this stands in for: programs/gzip.c:170-174 compress,
+ * :249-273 the multi-member decompress loop around libdeflate_gzip_decompress_ex).
+ * Host buffers; synchronous; every member is one chunk of the batch calls above.
+ *
+ * compress: 0 on success (then *out_nbytes is the file size); a CUDA error code;
+ *           or -1 when out_avail is too small (never for
+ *           out_avail >= libdeflate_b200_bgzf_compress_bound(in_nbytes)).
+ * decompress: 0 if the call ran; *result is LIBDEFLATE_SUCCESS, LIBDEFLATE_BAD_DATA
+ *           (not BGZF / corrupt member / CRC or size mismatch) or
+ *           LIBDEFLATE_INSUFFICIENT_SPACE; *actual_out = bytes written on SUCCESS.
+ */
+#define LIBDEFLATE_B200_BGZF_BLOCK 65280
+LIBDEFLATEAPI size_t
+libdeflate_b200_bgzf_compress_bound(size_t in_nbytes);
+LIBDEFLATEAPI int
+libdeflate_b200_bgzf_compress(struct libdeflate_b200_ctx *ctx, int level,
+			      const void *in, size_t in_nbytes,
+			      void *out, size_t out_avail, size_t *out_nbytes);
+LIBDEFLATEAPI int
+libdeflate_b200_bgzf_decompress(struct libdeflate_b200_ctx *ctx,
+				const void *in, size_t in_nbytes,
+				void *out, size_t out_avail,
+				size_t *actual_out, int32_t *result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,7 @@ BATCH_SYMBOLS = [
     "libdeflate_b200_decompress_batch", "libdeflate_b200_compress_batch",
     "libdeflate_b200_crc32_batch", "libdeflate_b200_adler32_batch",
     "libdeflate_b200_decompress_batch_host", "libdeflate_b200_compress_batch_host",
+    "libdeflate_b200_bgzf_compress_bound", "libdeflate_b200_bgzf_compress", "libdeflate_b200_bgzf_decompress",
 ]
 
 
@@ -143,6 +144,12 @@ def load_library(path=None):
     lib.libdeflate_b200_decompress_batch_host.argtypes = [P, c_int, c_uint, P, P, P, P, P, P, P, S]
     lib.libdeflate_b200_compress_batch_host.restype = c_int
     lib.libdeflate_b200_compress_batch_host.argtypes = [P, c_int, c_int, P, P, P, P, P, S]
+    lib.libdeflate_b200_bgzf_compress_bound.restype = S
+    lib.libdeflate_b200_bgzf_compress_bound.argtypes = [S]
+    lib.libdeflate_b200_bgzf_compress.restype = c_int
+    lib.libdeflate_b200_bgzf_compress.argtypes = [P, c_int, P, S, P, S, P]
+    lib.libdeflate_b200_bgzf_decompress.restype = c_int
+    lib.libdeflate_b200_bgzf_decompress.argtypes = [P, P, S, P, S, P, P]
     return lib
 
 
@@ -300,6 +307,26 @@ class Context:
             out.append(slab.raw[off:off + res[i]] if res[i] else None)
             off += avail[i]
         return out
+
+    def bgzf_compress(self, data, level=6, out_avail=None):
+        """One buffer -> blocked gzip file (bytes), or None if out_avail was too small."""
+        avail = self.l.libdeflate_b200_bgzf_compress_bound(len(data)) if out_avail is None else out_avail
+        out = ctypes.create_string_buffer(max(avail, 1))
+        n = c_size_t(0)
+        rc = self.l.libdeflate_b200_bgzf_compress(self.h, level, data, len(data), out, avail, ctypes.byref(n))
+        if rc == -1:
+            return None
+        self._check(rc, "bgzf_compress")
+        return out.raw[:n.value]
+
+    def bgzf_decompress(self, data, out_avail):
+        """Blocked gzip file -> (result, bytes or None)."""
+        out = ctypes.create_string_buffer(max(out_avail, 1))
+        n = c_size_t(0)
+        res = ctypes.c_int32(0)
+        self._check(self.l.libdeflate_b200_bgzf_decompress(self.h, data, len(data), out, out_avail, ctypes.byref(n), ctypes.byref(res)),
+                    "bgzf_decompress")
+        return res.value, (out.raw[:n.value] if res.value == 0 else None)
 
     def decompress_batch_host(self, streams, out_avail, fmt=RAW, exact=False):
         """Returns list of (result, bytes or None, actual_in, actual_out)."""

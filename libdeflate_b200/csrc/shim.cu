@@ -797,6 +797,129 @@ extern "C" int libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *c
 static void *(*g_malloc)(size_t) = malloc;
 static void (*g_free)(void *) = free;
 
+// ---- blocked gzip (BGZF) on top of the host batch calls ---------------------------------------
+// Host logic only: members are compressed / decompressed by the batch kernels as ordinary gzip
+// chunks; this layer cuts the input into blocks, rewrites each member's 10-byte header into the
+// 18-byte BGZF one (FEXTRA with the "BC" block-size subfield) and, on the way back, walks the BC
+// fields to find the members and their uncompressed sizes (ISIZE) without decoding anything.
+static const u8 LDB_BGZF_EOF[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 27, 0,
+				    3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+static size_t gzip_bound_of(size_t n) { return 5 * ((n + 4999) / 5000 ? (n + 4999) / 5000 : 1) + n + 18; }
+
+extern "C" size_t libdeflate_b200_bgzf_compress_bound(size_t in_nbytes)
+{
+	const size_t B = LIBDEFLATE_B200_BGZF_BLOCK;
+	const size_t full = in_nbytes / B, tail = in_nbytes % B;
+	size_t total = full * (gzip_bound_of(B) + 8) + sizeof(LDB_BGZF_EOF);
+	if (tail) total += gzip_bound_of(tail) + 8;
+	return total;
+}
+
+extern "C" int libdeflate_b200_bgzf_compress(struct libdeflate_b200_ctx *ctx, int level, const void *in, size_t in_nbytes,
+					      void *out, size_t out_avail, size_t *out_nbytes)
+{
+	const size_t B = LIBDEFLATE_B200_BGZF_BLOCK;
+	const size_t nblk = (in_nbytes + B - 1) / B;
+	const size_t slot = (gzip_bound_of(B) + 15) & ~(size_t)15;
+	*out_nbytes = 0;
+	size_t pos = 0;
+	u8 *o = (u8 *)out;
+	if (nblk) {
+		host_scratch tmp(nblk * slot), arrays(nblk * (2 * sizeof(void *) + 3 * sizeof(size_t)));
+		if (!tmp.p || !arrays.p) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
+		const void **ip = (const void **)arrays.p;
+		void **op = (void **)(ip + nblk);
+		size_t *isz = (size_t *)(op + nblk), *oav = isz + nblk, *osz = oav + nblk;
+		for (size_t i = 0; i < nblk; i++) {
+			ip[i] = (const u8 *)in + i * B;
+			isz[i] = i + 1 < nblk ? B : in_nbytes - i * B;
+			op[i] = (u8 *)tmp.p + i * slot;
+			oav[i] = slot;
+		}
+		int rc = libdeflate_b200_compress_batch_host(ctx, LIBDEFLATE_B200_GZIP, level, ip, isz, op, oav, osz, nblk);
+		if (rc) return rc;
+		for (size_t i = 0; i < nblk; i++) {
+			const u8 *m = (const u8 *)op[i];
+			if (osz[i] < 18) return ldb_fail(cudaErrorInvalidValue, "bgzf: member did not fit its bound", __FILE__, __LINE__);
+			const size_t total = osz[i] + 8;		// the header grows from 10 to 18 bytes
+			if (total > 65536) return ldb_fail(cudaErrorInvalidValue, "bgzf: member exceeds 64 KiB", __FILE__, __LINE__);
+			if (pos + total > out_avail) return -1;
+			u8 *h = o + pos;
+			h[0] = 0x1f; h[1] = 0x8b; h[2] = 8; h[3] = 4;	// FLG.FEXTRA
+			h[4] = h[5] = h[6] = h[7] = 0;			// MTIME
+			h[8] = m[8]; h[9] = 0xff;			// XFL as written by the kernel, OS unknown
+			h[10] = 6; h[11] = 0;				// XLEN
+			h[12] = 'B'; h[13] = 'C'; h[14] = 2; h[15] = 0;
+			h[16] = (u8)(total - 1); h[17] = (u8)((total - 1) >> 8);
+			memcpy(h + 18, m + 10, osz[i] - 10);
+			pos += total;
+		}
+	}
+	if (pos + sizeof(LDB_BGZF_EOF) > out_avail) return -1;
+	memcpy(o + pos, LDB_BGZF_EOF, sizeof(LDB_BGZF_EOF));
+	*out_nbytes = pos + sizeof(LDB_BGZF_EOF);
+	return 0;
+}
+
+extern "C" int libdeflate_b200_bgzf_decompress(struct libdeflate_b200_ctx *ctx, const void *in, size_t in_nbytes,
+						void *out, size_t out_avail, size_t *actual_out, int32_t *result)
+{
+	const u8 *p = (const u8 *)in;
+	*actual_out = 0;
+	*result = LDB_BAD_DATA;
+	// pass 1: walk the members (header + BC subfield + ISIZE), no decoding
+	size_t nblk = 0, total_out = 0;
+	for (int pass = 0; pass < 2; pass++) {
+		host_scratch arrays(pass ? (nblk ? nblk : 1) * (2 * sizeof(void *) + 3 * sizeof(size_t) + sizeof(int32_t)) : 1);
+		const void **ip = (const void **)arrays.p;
+		void **op = pass ? (void **)(ip + nblk) : nullptr;
+		size_t *isz = pass ? (size_t *)(op + nblk) : nullptr, *oav = pass ? isz + nblk : nullptr, *aout = pass ? oav + nblk : nullptr;
+		int32_t *res = pass ? (int32_t *)(aout + nblk) : nullptr;
+		if (pass && !arrays.p) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
+		size_t pos = 0, k = 0, opos = 0;
+		while (pos < in_nbytes) {
+			if (in_nbytes - pos < 18 + 8) return 0;
+			const u8 *h = p + pos;
+			if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+			const size_t xlen = h[10] | ((size_t)h[11] << 8);
+			if (12 + xlen + 8 > in_nbytes - pos) return 0;
+			size_t bsize = 0;
+			for (size_t x = 0; x + 4 <= xlen;) {		// subfields: SI1 SI2 LEN(2) data
+				const u8 *sf = h + 12 + x;
+				const size_t slen = sf[2] | ((size_t)sf[3] << 8);
+				if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (sf[4] | ((size_t)sf[5] << 8)) + 1;
+				x += 4 + slen;
+			}
+			if (bsize < 12 + xlen + 8 || bsize > in_nbytes - pos) return 0;
+			const u8 *t = h + bsize - 4;
+			const size_t isize = t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+			if (pass) {
+				ip[k] = h; isz[k] = bsize;
+				op[k] = (u8 *)out + opos; oav[k] = isize;
+			}
+			k++;
+			opos += isize;
+			pos += bsize;
+		}
+		if (!pass) {
+			nblk = k;
+			total_out = opos;
+			if (total_out > out_avail) { *result = LDB_INSUFFICIENT_SPACE; return 0; }
+			if (nblk == 0) { *result = LDB_SUCCESS; return 0; }
+			continue;
+		}
+		int rc = libdeflate_b200_decompress_batch_host(ctx, LIBDEFLATE_B200_GZIP, LIBDEFLATE_B200_EXACT_OUT_SIZE, ip, isz, op, oav,
+								nullptr, aout, res, nblk);
+		if (rc) return rc;
+		for (size_t i = 0; i < nblk; i++)
+			if (res[i] != LDB_SUCCESS) { *result = LDB_BAD_DATA; return 0; }
+	}
+	*actual_out = total_out;
+	*result = LDB_SUCCESS;
+	return 0;
+}
+
 extern "C" void libdeflate_set_memory_allocator(void *(*malloc_func)(size_t), void (*free_func)(void *))
 {
 	g_malloc = malloc_func;

@@ -240,3 +240,44 @@ def check_random_mix_round_trip(ctx, seed=1, rounds=3, per_round=8):
         outs = ctx.decompress_batch_host(zs, [len(c) for c in chunks], fmt)
         for c, o in zip(chunks, outs):
             assert o[0] == 0 and o[1] == c, ("own inflate", lvl, fmt, len(c))
+
+
+def bgzf_reference_file(data, level=6, block=65280):
+    """A BGZF file made with Python's zlib only (what bgzip / htslib write): test input for the decompressor."""
+    import struct
+    out = []
+    for off in range(0, len(data), block):
+        piece = data[off:off + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        payload = co.compress(piece) + co.flush()
+        bsize = 18 + len(payload) + 8
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize - 1) + payload
+                   + struct.pack("<II", zlib.crc32(piece), len(piece)))
+    out.append(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
+    return b"".join(out)
+
+
+def check_bgzf(ctx, sizes=(0, 1, 65279, 65280, 65281, 200000), levels=(1, 6)):
+    """One buffer <-> blocked gzip file: any gunzip reads ours, we read bgzip-style files, malformed files are
+    refused, too-small buffers are reported."""
+    import gzip
+    import corpus
+    for k, n in enumerate(sizes):
+        data = corpus.mixed(n, k) if k % 2 else corpus.text(n, k)
+        for lvl in levels:
+            f = ctx.bgzf_compress(data, lvl)
+            assert f is not None and len(f) <= ctx.l.libdeflate_b200_bgzf_compress_bound(n)
+            assert gzip.decompress(f) == data                      # an ordinary multi-member gzip file
+            assert f.endswith(bgzf_reference_file(b""))             # the BGZF end-of-file member
+            assert ctx.bgzf_decompress(f, n) == (0, data)
+            if n:
+                assert ctx.bgzf_decompress(f, n - 1)[0] == 3       # LIBDEFLATE_INSUFFICIENT_SPACE
+                assert ctx.bgzf_compress(data, lvl, out_avail=len(f) - 1) is None
+        ref = bgzf_reference_file(data)
+        assert ctx.bgzf_decompress(ref, n + 10) == (0, data)
+        if n > 100:
+            bad = bytearray(ref)
+            bad[len(bad) // 2] ^= 0x55                              # payload / CRC damage
+            assert ctx.bgzf_decompress(bytes(bad), n)[0] == 1      # LIBDEFLATE_BAD_DATA
+            assert ctx.bgzf_decompress(gzip.compress(data), n)[0] == 1   # plain gzip has no BC subfield
+            assert ctx.bgzf_decompress(ref[:-40], n)[0] == 1       # truncated

@@ -41,6 +41,10 @@ def test_deflate_random_mix_emulated(emu_ctx):
     pc.check_random_mix_round_trip(emu_ctx, seed=3, rounds=3)
 
 
+def test_bgzf_emulated(emu_ctx):
+    pc.check_bgzf(emu_ctx, sizes=(0, 1, 65280, 65281, 140000), levels=(6,))
+
+
 def test_inflate_output_primitives_unit():
     """Randomized unit test of the word-accumulator / match-copy primitives (host build)."""
     import os

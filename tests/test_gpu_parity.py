@@ -124,6 +124,10 @@ def test_compress_random_mix(gpu_ctx):
     pc.check_random_mix_round_trip(gpu_ctx, seed=7, rounds=12, per_round=24)
 
 
+def test_bgzf(gpu_ctx):
+    pc.check_bgzf(gpu_ctx, sizes=(0, 1, 65279, 65280, 65281, 200000, 3000000), levels=(1, 6, 9))
+
+
 def test_pipelined_host_path(gpu_ctx):
     import libdeflate_b200 as ldb
     pc.check_host_pipeline(ldb.lib(), gpu_ctx, n=8192, chunk=65536)
