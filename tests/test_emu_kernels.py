@@ -3,6 +3,7 @@
 This is test infrastructure (the dev container has no GPU); the product path is only
 ever the nvcc build, exercised by test_gpu_parity.py under `-m gpu`.
 """
+import pytest
 import parity_checks as pc
 
 
@@ -43,6 +44,26 @@ def test_deflate_random_mix_emulated(emu_ctx):
 
 def test_bgzf_emulated(emu_ctx):
     pc.check_bgzf(emu_ctx, sizes=(0, 1, 65280, 65281, 140000), levels=(6,))
+
+
+def test_gz_front_end_emulated(emu_ctx, tmp_path):
+    """The gzip-style front end (python -m libdeflate_b200.gz) on the emulated library: files written by it
+    are read by Python's gzip, files it reads back are identical, -k / -c / level flags behave."""
+    import gzip
+    import corpus
+    from libdeflate_b200 import gz
+    data = corpus.text(150000, 9) + corpus.rand(5000, 9)
+    f = tmp_path / "a.txt"
+    f.write_bytes(data)
+    assert gz.main(["-9", "-k", str(f)], ctx=emu_ctx) == 0
+    packed = (tmp_path / "a.txt.gz").read_bytes()
+    assert f.exists() and gzip.decompress(packed) == data and gz.uncompressed_size(packed) == len(data)
+    f.unlink()
+    assert gz.main(["-d", str(tmp_path / "a.txt.gz")], ctx=emu_ctx) == 0
+    assert f.read_bytes() == data and not (tmp_path / "a.txt.gz").exists()
+    assert gz.decompress_bytes(emu_ctx, pc.bgzf_reference_file(data)) == data
+    with pytest.raises(ValueError):
+        gz.decompress_bytes(emu_ctx, gzip.compress(data))
 
 
 def test_inflate_output_primitives_unit():
