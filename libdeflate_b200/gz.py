@@ -49,7 +49,27 @@ def decompress_bytes(ctx, data):
     return out
 
 
-def main(argv=None, ctx=None):
+def decompress_members(api, data):
+    """Any multi-member gzip file, one member at a time through libdeflate_gzip_decompress_ex -- the loop of
+    programs/gzip.c:249-273 (output buffer doubled on INSUFFICIENT_SPACE, next member at actual_in).  Every
+    member is a single stream, i.e. one lane of the GPU: correct, not fast; blocked files go through
+    decompress_bytes()."""
+    out, pos = [], 0
+    while pos < len(data):
+        avail = max(4 * (len(data) - pos), 1 << 16)
+        while True:
+            res, piece, ain, _aout = api.decompress(data[pos:], avail, ldb.GZIP)
+            if res != 3:        # LIBDEFLATE_INSUFFICIENT_SPACE
+                break
+            avail *= 2
+        if res != 0:
+            raise ValueError("decompression failed: libdeflate_result %d at byte %d" % (res, pos))
+        out.append(piece)
+        pos += ain
+    return b"".join(out)
+
+
+def main(argv=None, ctx=None, api=None):
     ap = argparse.ArgumentParser(prog="python -m libdeflate_b200.gz", description=__doc__.split("\n\n")[1])
     ap.add_argument("-d", "--decompress", action="store_true")
     ap.add_argument("-c", "--stdout", action="store_true")
@@ -63,7 +83,10 @@ def main(argv=None, ctx=None):
     for path in args.files:
         data = open(path, "rb").read()
         if args.decompress:
-            out = decompress_bytes(ctx, data)
+            try:
+                out = decompress_bytes(ctx, data)
+            except ValueError:
+                out = decompress_members(api or ldb.Api(), data)     # not blocked: member by member
             dst = path[:-3] if path.endswith(".gz") else path + ".out"
         else:
             out = compress_bytes(ctx, data, level)

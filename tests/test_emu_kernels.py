@@ -46,7 +46,7 @@ def test_bgzf_emulated(emu_ctx):
     pc.check_bgzf(emu_ctx, sizes=(0, 1, 65280, 65281, 140000), levels=(6,))
 
 
-def test_gz_front_end_emulated(emu_ctx, tmp_path):
+def test_gz_front_end_emulated(emu_ctx, emu_api, tmp_path):
     """The gzip-style front end (python -m libdeflate_b200.gz) on the emulated library: files written by it
     are read by Python's gzip, files it reads back are identical, -k / -c / level flags behave."""
     import gzip
@@ -64,6 +64,12 @@ def test_gz_front_end_emulated(emu_ctx, tmp_path):
     assert gz.decompress_bytes(emu_ctx, pc.bgzf_reference_file(data)) == data
     with pytest.raises(ValueError):
         gz.decompress_bytes(emu_ctx, gzip.compress(data))
+    # ordinary (not blocked) multi-member files go member by member through the classic API
+    plain = gzip.compress(data[:70000], 6) + gzip.compress(b"") + gzip.compress(data[70000:], 1)
+    assert gz.decompress_members(emu_api, plain) == data
+    g = tmp_path / "b.gz"
+    g.write_bytes(plain)
+    assert gz.main(["-d", "-k", str(g)], ctx=emu_ctx, api=emu_api) == 0 and (tmp_path / "b").read_bytes() == data
 
 
 def test_inflate_output_primitives_unit():
