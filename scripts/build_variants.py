@@ -13,14 +13,11 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    "i_base": [],
-    "i_r3": ["-DINF_LIT_ROUNDS=3"],
-    "i_r6": ["-DINF_LIT_ROUNDS=6"],
-    "i_m4": ["-DINF_LIT_MIN_LANES=4"],
-    "i_m16": ["-DINF_LIT_MIN_LANES=16"],
-    "i_c32": ["-DINF_COPY_CHUNK=32"],
-    "i_c8": ["-DINF_COPY_CHUNK=8"],
-    "i_r6m16": ["-DINF_LIT_ROUNDS=6", "-DINF_LIT_MIN_LANES=16"],
+    # A/B still to run (round 2): resumable chain walk, identical output, verified in the emulator only
+    "q0": [],
+    "q6": ["-DLZ_QUANTUM=6"],
+    "q8": ["-DLZ_QUANTUM=8"],
+    "q12": ["-DLZ_QUANTUM=12"],
 }
 
 

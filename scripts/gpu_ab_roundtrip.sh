@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in prev dbl prev dbl dbltim; do
+for v in q0 q6 q8 q12 q0; do
   echo "== $v"
   timeout 300 python scripts/variant_bench.py $v roundtrip 16384 2> gpurun_out/var_$v.err | python -c "
 import sys, json
