@@ -35,7 +35,7 @@ NCHUNKS_DEFAULT = 65536
 LEVEL = 6
 SYNTH_SO = os.path.join(ROOT, "bench", "libsynth.so")
 CPUB_SO = os.path.join(ROOT, "oracle", "_ref", "libcpubench.so")
-KIND = {"crc32": 0, "adler32": 1, "inflate": 2, "verify": 3, "deflate": 4}
+KIND = {"crc32": 0, "adler32": 1, "inflate": 2, "verify": 3, "deflate": 4, "resolve": 5}
 
 
 def load_peaks():

@@ -16,7 +16,9 @@
  * "e2e").
  *
  * All calls are asynchronous on the context's stream unless stated; use
- * libdeflate_b200_ctx_sync().  Return value: 0 on success, otherwise a CUDA
+ * libdeflate_b200_ctx_sync().  (libdeflate_b200_decompress_batch waits once, early, for the
+ * stream: it reads the chunk sizes back to size its scratch; its kernels are then queued
+ * asynchronously like everything else.)  Return value: 0 on success, otherwise a CUDA
  * error code (cudaError_t) -- no silent fallback exists.
  */
 #ifndef LIBDEFLATE_B200_H
@@ -75,7 +77,8 @@ LIBDEFLATEAPI double libdeflate_b200_timer_stop_ms(struct libdeflate_b200_ctx *c
 /* Per-kernel device time: with profiling on, every kernel launch is bracketed by two
  * events on the context's stream.  kernel_time_ms() synchronises, then returns the summed
  * duration (ms) and launch count of one kind since the last reset.
- * kind: 0 crc32, 1 adler32, 2 inflate, 3 trailer-verify, 4 deflate. */
+ * kind: 0 crc32, 1 adler32, 2 inflate decode (Huffman -> tokens), 3 trailer-verify, 4 deflate,
+ *       5 inflate resolve (tokens -> bytes). */
 LIBDEFLATEAPI void   libdeflate_b200_ctx_set_profiling(struct libdeflate_b200_ctx *ctx, int on);
 LIBDEFLATEAPI double libdeflate_b200_kernel_time_ms(struct libdeflate_b200_ctx *ctx, int kind, uint64_t *n_launches);
 LIBDEFLATEAPI void   libdeflate_b200_kernel_time_reset(struct libdeflate_b200_ctx *ctx);

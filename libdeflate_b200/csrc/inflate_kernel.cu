@@ -8,8 +8,19 @@
 // the enum libdeflate_result verdict, actual_in and actual_out.  Only those are
 // contractual; table geometry, refill policy and scheduling below are ours.
 //
-// B200 mapping -- "one lane per stream", because Huffman decoding is a bit-serial
-// dependency chain and only issue slots spent on *different* streams add up:
+// Two kernels (this file = the first):
+//   ldb_inflate_decode_kernel  -- Huffman decoding only, "one lane per stream"; the decoded
+//       symbols leave as a TOKEN STREAM per chunk (literal bytes packed from the front of the
+//       chunk's scratch slot, 4-byte {literal run, length, offset} records from its back, format
+//       in ldb_common.cuh).  Every verdict, actual_in and actual_out are decided here: the
+//       decoder tracks the output position, so "offset > bytes produced" and "no room" need no
+//       output bytes.  No LZ77 window is touched -- with ~71 K streams in flight the windows
+//       (4.6 GB) can live nowhere but DRAM, which is what bound the one-kernel design of round 1.
+//   ldb_inflate_resolve_kernel (inflate_resolve.cu) -- one CTA per chunk turns the tokens into
+//       bytes inside a shared-memory window.
+//
+// B200 mapping of the decode kernel -- "one lane per stream", because Huffman decoding is a
+// bit-serial dependency chain and only issue slots spent on *different* streams add up:
 //   * a warp decodes 32 independent chunks at once, one per lane; a lane that
 //     finishes its chunk pulls the next chunk index from a global counter, so
 //     lanes never idle on a tail;
@@ -24,12 +35,10 @@
 //     per-lane global scratch (L1/L2 resident);
 //   * block headers are parsed by the owning lane, then the WARP builds that
 //     lane's tables cooperatively (ballot/match_any ranking, strided fills);
-//   * stored blocks are copied by the whole warp, coalesced;
+//   * stored blocks are copied into the literal stream by the whole warp, coalesced;
 //   * compressed input is consumed through 4-byte aligned loads with one word
-//     of lookahead per lane; output is gathered in a per-lane 8-byte accumulator
-//     and written with aligned 8-byte stores; match sources are fetched with
-//     aligned 8-byte loads + funnel shifts (offset >= 8) or expanded in
-//     registers from the periodic pattern (offset < 8).
+//     of lookahead per lane; literals are gathered four at a time and leave as aligned
+//     4-byte stores, a match is ONE 4-byte record store.
 //
 // Verdict rules restated from the reference in terms of P = number of input bits
 // consumed and n = in_nbytes (see DESIGN.md "verdict algebra"):
@@ -44,8 +53,9 @@
 //     bytes must exist, LEN == ~NLEN, then room (INSUFFICIENT_SPACE), then LEN
 //     bytes must exist (decompress_template.h:255-283).
 //
-// Algorithmic HBM bytes per chunk: in_nbytes (read once) + actual_out (written
-// once).  Back-reference reads are window traffic served by L1/L2.
+// Algorithmic HBM bytes per chunk (both kernels together): in_nbytes (read once) + actual_out
+// (written once).  The token stream (~1.5 x in_nbytes written here, read by the resolve kernel)
+// is extra traffic of the two-kernel split and is reported as such (bench.py "traffic").
 #include "ldb_common.cuh"
 
 // table geometry (overridable at build time for tuning sweeps, see scripts/build_variants.py)
@@ -120,18 +130,21 @@ struct inf_lane {
 	u32 wpos;		// byte offset of w0 relative to in_al (multiple of 4; may pass in_nal: virtual zeros)
 	u32 w0, w1, w2;
 	u32 bitpos;		// bits of w0 already consumed
-	// output: bytes are gathered into aligned 4-byte words
-	u8 *out;
-	u32 out_pos;
+	// token output: literal bytes are gathered into aligned 4-byte words of the literal stream,
+	// records are written downwards from the end of the chunk's slot
+	u8 *lit;		// literal stream (16-byte aligned)
+	u32 *rec_end;		// one past the slot's last u32; record j lives at rec_end[-1 - j]
+	u32 n_lit;		// literal bytes emitted (the low two bits count the bytes pending in acc)
+	u32 n_rec;
+	u32 litrun;		// literals since the last record
+	u32 out_pos;		// bytes the stream has produced so far
 	u32 out_avail;
-	u32 acc;		// the cnt (< 4) pending bytes of the current output word
-	u32 cnt;
+	u32 acc;		// the (n_lit & 3) pending bytes of the current literal word
 	// block state
 	u32 state;
 	u32 is_final;
 	u32 hlit, hdist, is_static;
 	u32 stored_len, stored_src;
-	u32 copy_rem, copy_off;	// match bytes still to be copied (continued across iterations)
 	u32 pend_len;		// decoded match length whose offset has not been decoded yet
 	// bookkeeping
 	u32 chunk;		// chunk index
@@ -193,149 +206,49 @@ __device__ __forceinline__ u64 inf_bits_consumed(const inf_lane &s)
 	return (u64)s.wpos * 8 + s.bitpos - 8 * s.in_a0;
 }
 
-// ---- output -------------------------------------------------------------------
-// pos_end = out position just past the word's last byte; the word is 4-byte aligned in
-// memory by construction.  Only the very first word of a chunk can start before 'out'.
-__device__ __forceinline__ void inf_store_word(const inf_lane &s, u32 pos_end, u32 w)
-{
-	if (pos_end >= 4) {
-		*(u32 *)(s.out + pos_end - 4) = w;
-	} else {
-		for (u32 j = 4 - pos_end; j < 4; j++) s.out[pos_end - 4 + j] = (u8)(w >> (8 * j));
-	}
-}
-
+// ---- token output ---------------------------------------------------------------
 __device__ __forceinline__ void inf_put_byte(inf_lane &s, u32 b)
 {
-	s.acc |= b << (8 * s.cnt);
-	s.cnt++;
+	s.acc |= b << (8 * (s.n_lit & 3));
+	s.n_lit++;
+	s.litrun++;
 	s.out_pos++;
-	if (s.cnt == 4) {
-		inf_store_word(s, s.out_pos, s.acc);
+	if ((s.n_lit & 3) == 0) {
+		*(u32 *)(s.lit + s.n_lit - 4) = s.acc;
 		s.acc = 0;
-		s.cnt = 0;
 	}
 }
 
-__device__ __forceinline__ void inf_put_word(inf_lane &s, u32 w)
-{
-	u32 sh = 8 * s.cnt;
-	s.out_pos += 4;
-	inf_store_word(s, s.out_pos - s.cnt, s.acc | (w << sh));
-	s.acc = __funnelshift_rc(w, 0, 32 - sh);	// the cnt bytes of w that did not fit
-}
-
-// r in 1..3 bytes (already masked)
-__device__ __forceinline__ void inf_put_bytes(inf_lane &s, u32 w, u32 r)
-{
-	u32 sh = 8 * s.cnt;
-	u32 lo = s.acc | (w << sh);
-	s.out_pos += r;
-	u32 c = s.cnt + r;
-	if (c >= 4) {
-		c -= 4;
-		inf_store_word(s, s.out_pos - c, lo);
-		s.acc = __funnelshift_rc(w, 0, 32 - sh);
-	} else {
-		s.acc = lo;
-	}
-	s.cnt = c;
-}
-
-// make the pending bytes visible in memory (needed before reading them back)
+// the pending literal bytes go to memory (the word's upper bytes are scratch: the slot has slack)
 __device__ __forceinline__ void inf_flush_pending(const inf_lane &s)
 {
-	for (u32 j = 0; j < s.cnt; j++) {
-		int pos = (int)s.out_pos - (int)s.cnt + (int)j;
-		if (pos >= 0) s.out[pos] = (u8)(s.acc >> (8 * j));
-	}
+	if (s.n_lit & 3) *(u32 *)(s.lit + (s.n_lit & ~3u)) = s.acc;
 }
 
-// after bytes were written behind our back (stored blocks): reload the pending bytes
+// after literal bytes were written behind our back (stored blocks): reload the pending bytes
 __device__ __forceinline__ void inf_reload_pending(inf_lane &s)
 {
-	s.cnt = (u32)((uintptr_t)s.out + s.out_pos) & 3;
+	u32 c = s.n_lit & 3;
 	s.acc = 0;
-	for (u32 j = 0; j < s.cnt; j++) {
-		int pos = (int)s.out_pos - (int)s.cnt + (int)j;
-		if (pos >= 0) s.acc |= (u32)(*(volatile u8 *)(s.out + pos)) << (8 * j);
-	}
+	if (c) s.acc = *(volatile u32 *)(s.lit + (s.n_lit & ~3u)) & ((1u << (8 * c)) - 1);
 }
 
-// Copies 'length' (<= INF_COPY_CHUNK) bytes of a match.  Long matches are continued by the
-// caller in later iterations so that one long match does not stall the other 31 lanes.
-#ifndef INF_COPY_CHUNK
-#define INF_COPY_CHUNK 16
-#endif
-__device__ __forceinline__ void inf_copy_chunk(inf_lane &s, u32 length, u32 offset)
+__device__ __forceinline__ void inf_put_record(inf_lane &s, u32 r)
 {
-	if (offset >= 24) {
-		// far source: all (<= 5) source words are complete in memory before this chunk
-		// starts (offset >= 20 + cnt), so they are loaded up front, one latency per chunk
-		const u8 *a = s.out + (s.out_pos - offset);
-		const u32 *A = (const u32 *)((uintptr_t)a & ~(uintptr_t)3);
-		const u32 sh = 8 * ((u32)(uintptr_t)a & 3);
-		const u32 nw = (length + 3) >> 2;	// output steps
-		u32 w0 = A[0], w1 = A[1], w2 = 0, w3 = 0, w4 = 0;
-		if (nw > 1) w2 = A[2];
-		if (nw > 2) w3 = A[3];
-		if (nw > 3) w4 = A[4];
-		u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
-		u32 v2 = __funnelshift_r(w2, w3, sh), v3 = __funnelshift_r(w3, w4, sh);
-		if (length >= 4) inf_put_word(s, v0);
-		if (length >= 8) inf_put_word(s, v1);
-		if (length >= 12) inf_put_word(s, v2);
-		if (length >= 16) inf_put_word(s, v3);
-		u32 r = length & 3;
-		if (r) {
-			u32 t = length < 4 ? v0 : (length < 8 ? v1 : (length < 12 ? v2 : v3));
-			inf_put_bytes(s, t & ((1u << (8 * r)) - 1), r);
-		}
-	} else if (offset >= 8) {
-		// near source: a source word is only complete once the previous output word has
-		// been stored (offset >= 4 + cnt), so load right before use
-		const u8 *a = s.out + (s.out_pos - offset);
-		const u32 *A = (const u32 *)((uintptr_t)a & ~(uintptr_t)3);
-		const u32 sh = 8 * ((u32)(uintptr_t)a & 3);
-		u32 lo = A[0];
-		while (length >= 4) {
-			u32 hi = *(const volatile u32 *)(A + 1);
-			inf_put_word(s, __funnelshift_r(lo, hi, sh));
-			lo = hi;
-			A++;
-			length -= 4;
-		}
-		if (length) {
-			u32 hi = *(const volatile u32 *)(A + 1);
-			inf_put_bytes(s, __funnelshift_r(lo, hi, sh) & ((1u << (8 * length)) - 1), length);
-		}
-	} else {
-		// periodic source: expand the last 'offset' bytes in registers
-		inf_flush_pending(s);
-		u64 cur = 0;
-		for (u32 j = 0; j < offset; j++) cur |= (u64)s.out[s.out_pos - offset + j] << (8 * j);
-		u32 ob = 8 * offset;
-		cur |= cur << ob;
-		if (2 * ob < 64) cur |= cur << (2 * ob);
-		if (4 * ob < 64) cur |= cur << (4 * ob);
-		const u32 r = offset == 3 ? 1 : (offset > 4 ? 4 : 0);	// 4 mod offset
-		while (length >= 4) {
-			inf_put_word(s, (u32)cur);
-			if (r) cur = (cur >> (8 * r)) | (cur << (8 * (offset - r)));
-			length -= 4;
-		}
-		if (length) inf_put_bytes(s, (u32)cur & ((1u << (8 * length)) - 1), length);
-	}
+	s.n_rec++;
+	*(s.rec_end - s.n_rec) = r;
 }
 
-// whole match at once (unit tests)
-__device__ __forceinline__ void inf_copy_match(inf_lane &s, u32 length, u32 offset)
+// a match of 'length' bytes at distance 'offset', preceded by the literals since the last record
+__device__ __forceinline__ void inf_put_match(inf_lane &s, u32 length, u32 offset)
 {
-	while (length) {
-		u32 n = length < INF_COPY_CHUNK ? length : INF_COPY_CHUNK;
-		inf_copy_chunk(s, n, offset);
-		length -= n;
+	if (s.litrun > 255) {
+		inf_put_record(s, LDB_TOK_PURE_FLAG | s.litrun);
+		s.litrun = 0;
 	}
+	inf_put_record(s, (s.litrun << 23) | ((length - 3) << 15) | (offset - 1));
+	s.litrun = 0;
+	s.out_pos += length;
 }
 
 // ---- wrapper headers ------------------------------------------------------------
@@ -737,7 +650,7 @@ __device__ __forceinline__ int inf_decode_litlen(inf_lane &s, const u8 *sm, cons
 	return LDB_SUCCESS;
 }
 
-// inf_decode_offset: the offset of the pending length; arms the copy.
+// inf_decode_offset: the offset of the pending length; emits the match record.
 __device__ __forceinline__ int inf_decode_offset(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
 {
 	const u16 *otab = (const u16 *)(sm + INF_SM_OTAB);
@@ -764,18 +677,17 @@ __device__ __forceinline__ int inf_decode_offset(inf_lane &s, const u8 *sm, cons
 		s.bitpos += eb;
 	}
 	if (offset > s.out_pos) return LDB_BAD_DATA;
-	s.copy_rem = s.pend_len;
-	s.copy_off = offset;
+	inf_put_match(s, s.pend_len, offset);
 	s.pend_len = 0;
 	return LDB_SUCCESS;
 }
 
-// ---- the kernel ---------------------------------------------------------------------
+// ---- the decode kernel --------------------------------------------------------------
 // The warps of a CTA are independent (each has its own tables and never syncs with the others);
 // INF_WPC of them share a CTA only because shared memory is reserved per CTA (1 KiB each), and
 // 3 CTAs x 5 warps fit where 15 single-warp CTAs would not.
 __global__ void __launch_bounds__(32 * INF_WPC)
-ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
+ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 {
 	LDB_DYN_SMEM(sm_cta);
 	u8 *sm = sm_cta + (threadIdx.x >> 5) * INF_SM_BYTES;
@@ -787,8 +699,8 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 	s.state = ST_IDLE;
 	s.chunk = 0xffffffffu;
 	s.in = nullptr; s.in_al = nullptr; s.in_a0 = 0; s.in_n = 0; s.in_nal = 0; s.wpos = 0; s.w0 = 0; s.w1 = 0; s.w2 = 0; s.bitpos = 0;
-	s.out = nullptr; s.out_pos = 0; s.out_avail = 0; s.acc = 0; s.cnt = 0;
-	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.copy_rem = 0; s.copy_off = 0; s.pend_len = 0;
+	s.lit = nullptr; s.rec_end = nullptr; s.n_lit = 0; s.n_rec = 0; s.litrun = 0; s.out_pos = 0; s.out_avail = 0; s.acc = 0;
+	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.pend_len = 0;
 	bool exhausted = false;
 
 	// finishes the lane's stream with 'verdict' and makes the lane idle
@@ -796,7 +708,6 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 		const size_t c = s.chunk;
 		u32 footer = a.format == LDB_FMT_GZIP ? 8 : (a.format == LDB_FMT_ZLIB ? 4 : 0);
 		if (verdict == LDB_SUCCESS) {
-			inf_flush_pending(s);
 			u64 P = inf_bits_consumed(s);
 			if (P > (u64)s.in_n * 8) verdict = LDB_BAD_DATA;	// decompress_template.h:754
 			else {
@@ -815,7 +726,17 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 				}
 			}
 		}
-		if (verdict != LDB_SUCCESS && verdict != LDB_SHORT_OUTPUT) a.actual_out[c] = 0;
+		if (verdict == LDB_SUCCESS || verdict == LDB_SHORT_OUTPUT) {
+			// the whole stream decoded: hand its tokens to the resolve kernel
+			inf_flush_pending(s);
+			if (s.litrun) inf_put_record(s, LDB_TOK_PURE_FLAG | s.litrun);
+			a.tok_counts[2 * c] = s.n_rec;
+			a.tok_counts[2 * c + 1] = s.n_lit;
+		} else {
+			a.actual_out[c] = 0;
+			a.tok_counts[2 * c] = 0;	// output contents are undefined on failure (libdeflate.h:216-217)
+			a.tok_counts[2 * c + 1] = 0;
+		}
 		a.results[c] = verdict;
 		s.state = ST_IDLE;
 	};
@@ -830,24 +751,29 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 			base = __shfl_sync(LDB_FULL_MASK, base, __ffs(idle) - 1);
 			if (s.state == ST_IDLE && !exhausted) {
 				size_t c = (size_t)base + __popc(idle & ((1u << lane) - 1));
-				if (c >= a.n) {
+				if (c >= a.count) {
 					exhausted = true;
 				} else {
+					c += a.first;
 					s.chunk = (u32)c;
 					const u8 *in = (const u8 *)a.in_ptrs[c];
 					size_t n = a.in_nbytes[c];
-					s.out = (u8 *)a.out_ptrs[c];
 					size_t oa = a.out_avail[c];
 					s.out_avail = oa > 0xfffffff0u ? 0xfffffff0u : (u32)oa;
 					s.out_pos = 0;
 					s.acc = 0;
-					s.copy_rem = 0;
 					s.pend_len = 0;
-					s.cnt = (u32)(uintptr_t)s.out & 3;	// the first word may start before 'out'
+					s.lit = a.tok_base + (a.tok_off[c] - a.tok_origin);
+					s.rec_end = (u32 *)(a.tok_base + (a.tok_off[c + 1] - a.tok_origin));
+					s.n_lit = 0;
+					s.n_rec = 0;
+					s.litrun = 0;
 					u32 footer;
 					u32 hdr = inf_parse_wrapper(in, n, a.format, &footer);
 					if (hdr == 0xffffffffu) {
 						a.actual_out[c] = 0;
+						a.tok_counts[2 * c] = 0;
+						a.tok_counts[2 * c + 1] = 0;
 						a.results[c] = LDB_BAD_DATA;
 					} else {
 						size_t dn = n - hdr - footer;
@@ -875,20 +801,24 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 		}
 		__syncwarp();
 
-		// (3) stored blocks: warp-wide coalesced copy, one lane's block at a time
+		// (3) stored blocks: their bytes are literals; warp-wide coalesced copy into the literal
+		// stream, one lane's block at a time
 		u32 stored = __ballot_sync(LDB_FULL_MASK, s.state == ST_STORED);
 		while (stored) {
 			u32 owner = __ffs(stored) - 1;
 			stored &= stored - 1;
-			// the owner's pending output bytes must be in memory first
+			// the owner's pending literal bytes must be in memory first
 			if (lane == owner) inf_flush_pending(s);
+			__syncwarp();
 			const u8 *src = (const u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.in + s.stored_src), owner);
-			u8 *dst = (u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.out + s.out_pos), owner);
+			u8 *dst = (u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.lit + s.n_lit), owner);
 			u32 len = __shfl_sync(LDB_FULL_MASK, s.stored_len, owner);
 			for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
 			__syncwarp();
 			if (lane == owner) {
 				s.out_pos += len;
+				s.n_lit += len;
+				s.litrun += len;
 				inf_reload_pending(s);
 				u32 next = s.stored_src + len;
 				inf_bits_init(s, next);	// P = 8 * next exactly
@@ -933,25 +863,19 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 			// of their block); stops early once most lanes wait for the match round
 #pragma unroll 1
 			for (int r = 0; r < INF_LIT_ROUNDS; r++) {
-				if (s.state == ST_DECODE && s.pend_len == 0 && s.copy_rem == 0) {
+				if (s.state == ST_DECODE && s.pend_len == 0) {
 					int v = inf_decode_litlen(s, sm, ovf, lane);
 					if (v != LDB_SUCCESS) finish(v);
 					else if (s.state == ST_HEADER && s.is_final) finish(LDB_SUCCESS);
 				}
 				if (r + 1 < INF_LIT_ROUNDS &&
-				    __popc(__ballot_sync(LDB_FULL_MASK, s.state == ST_DECODE && s.pend_len == 0 && s.copy_rem == 0)) < INF_LIT_MIN_LANES)
+				    __popc(__ballot_sync(LDB_FULL_MASK, s.state == ST_DECODE && s.pend_len == 0)) < INF_LIT_MIN_LANES)
 					break;
 			}
-			// match round: offsets of the pending lengths, then one bounded piece of every
-			// pending copy
+			// match round: the offsets of the pending lengths, one record each
 			if (s.state == ST_DECODE && s.pend_len) {
 				int v = inf_decode_offset(s, sm, ovf, lane);
 				if (v != LDB_SUCCESS) finish(v);
-			}
-			if (s.state == ST_DECODE && s.copy_rem) {
-				u32 nb = s.copy_rem < INF_COPY_CHUNK ? s.copy_rem : INF_COPY_CHUNK;
-				inf_copy_chunk(s, nb, s.copy_off);
-				s.copy_rem -= nb;
 			}
 			if ((it & 15) == 15 && !__any_sync(LDB_FULL_MASK, s.state == ST_DECODE)) break;
 		}
@@ -964,7 +888,8 @@ ldb_inflate_kernel(ldb_inflate_args a, u32 *work_counter)
 __global__ void ldb_verify_trailer_kernel(ldb_inflate_args a, const u32 *checksums)
 {
 	size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= a.n) return;
+	if (c >= a.count) return;
+	c += a.first;
 	if (a.results[c] != LDB_SUCCESS) return;
 	if (checksums[c] != a.trailer_expect[c]) {
 		a.results[c] = LDB_BAD_DATA;
@@ -976,20 +901,23 @@ __global__ void ldb_verify_trailer_kernel(ldb_inflate_args a, const u32 *checksu
 
 int ldb_launch_inflate(const ldb_inflate_args &a, const ldb_launch_cfg &cfg, void *stream)
 {
-	if (a.n == 0) return 0;
-	static bool attr_set = false;
-	if (!attr_set) {
-		LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_WPC * INF_SM_BYTES));
-		attr_set = true;
-	}
+	if (a.count == 0) return 0;
+	// the attribute is per device and cheap to set: every launch does it (a context may live on any GPU)
+	LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_WPC * INF_SM_BYTES));
 	u32 *counter = (u32 *)(a.overflow_scratch + (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream());
-	LDB_CUDA_CHECK_RET(cudaMemsetAsync(counter, 0, sizeof(u32), (cudaStream_t)stream));
-	size_t blocks = (a.n + 32 * INF_WPC - 1) / (32 * INF_WPC);
+	LDB_CUDA_CHECK_RET(cudaMemsetAsync(counter, 0, 2 * sizeof(u32), (cudaStream_t)stream));
+	size_t blocks = (a.count + 32 * INF_WPC - 1) / (32 * INF_WPC);
 	size_t cap = (size_t)ldb_inflate_grid_blocks(cfg) / INF_WPC;
 	if (blocks > cap) blocks = cap;
-	LDB_LAUNCH(ldb_inflate_kernel, dim3((unsigned)blocks), dim3(32 * INF_WPC), INF_WPC * INF_SM_BYTES, (cudaStream_t)stream, a, counter);
+	LDB_LAUNCH(ldb_inflate_decode_kernel, dim3((unsigned)blocks), dim3(32 * INF_WPC), INF_WPC * INF_SM_BYTES, (cudaStream_t)stream, a, counter);
 	LDB_CUDA_CHECK_RET(cudaGetLastError());
 	return 0;
+}
+
+// work counter of the resolve kernel (zeroed by ldb_launch_inflate together with the decoder's)
+u32 *ldb_inflate_resolve_counter(const ldb_inflate_args &a, const ldb_launch_cfg &cfg)
+{
+	return (u32 *)(a.overflow_scratch + (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream()) + 1;
 }
 
 // Number of WARPS (= groups of 32 concurrently decoded streams) the launch keeps resident.
@@ -1008,8 +936,8 @@ size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg)
 
 int ldb_launch_verify_trailer(const ldb_inflate_args &a, const u32 *d_checksums, void *stream)
 {
-	if (a.n == 0) return 0;
-	unsigned blocks = (unsigned)((a.n + 255) / 256);
+	if (a.count == 0) return 0;
+	unsigned blocks = (unsigned)((a.count + 255) / 256);
 	LDB_LAUNCH(ldb_verify_trailer_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, a, d_checksums);
 	LDB_CUDA_CHECK_RET(cudaGetLastError());
 	return 0;

@@ -91,9 +91,16 @@ int ldb_launch_crc32(const ldb_crc_tables *d_tables, const void *const *d_ptrs, 
 int ldb_launch_adler32(const void *const *d_ptrs, const size_t *d_nbytes, const u32 *d_init,
 		       u32 *d_values, size_t n, const ldb_launch_cfg &cfg, void *stream);
 
-// Inflate: per-chunk results in d_results; d_trailer_expect (optional) receives the
-// checksum stored in the zlib/gzip trailer and d_isize_expect the gzip ISIZE, for the
-// verify kernel that runs after the checksum kernel.
+// Inflate runs in two kernels:
+//   decode  (ldb_inflate_decode_kernel):  one lane per stream, Huffman decoding only; emits a
+//           TOKEN STREAM per chunk into a global scratch -- the literal bytes, packed, from the
+//           front of the chunk's slot and 4-byte records from its back -- and all verdicts;
+//   resolve (ldb_inflate_resolve_kernel): one CTA per chunk, places literals and LZ77 copies in
+//           a shared-memory window and writes the output in 16-byte coalesced rows.
+// Record format (u32): bit 31 set -> "literal run only", bits 30..0 = number of literals;
+// else bits 30..23 = literals preceding the match (0..255), bits 22..15 = length - 3,
+// bits 14..0 = offset - 1.
+#define LDB_TOK_PURE_FLAG 0x80000000u
 struct ldb_inflate_args {
 	const void *const *in_ptrs;
 	const size_t *in_nbytes;
@@ -105,11 +112,22 @@ struct ldb_inflate_args {
 	u32 *trailer_expect;	// scratch, n entries (zlib/gzip only)
 	u32 *isize_expect;	// scratch, n entries (gzip only)
 	u8 *overflow_scratch;	// per-stream overflow table space
+	// token scratch of this wave: chunk c owns bytes [tok_off[c], tok_off[c+1]) - tok_origin of tok_base
+	u8 *tok_base;
+	const u64 *tok_off;	// n + 1 entries (exclusive prefix sums of the per-chunk slot sizes)
+	u64 tok_origin;		// tok_off[first]
+	u32 *tok_counts;	// 2 per chunk: {records, literal bytes}; {0, 0} = nothing to resolve
+	size_t first;		// chunk range [first, first + count) of this wave
+	size_t count;
 	size_t n;
 	int format;
 	unsigned flags;
 };
+int ldb_launch_inflate_caps(const size_t *d_in_nbytes, const size_t *d_out_avail, u64 *d_tok_off, size_t n, void *stream);
+size_t ldb_inflate_tok_cap(size_t in_nbytes, size_t out_avail);	// host copy of the slot size formula
 int ldb_launch_inflate(const ldb_inflate_args &a, const ldb_launch_cfg &cfg, void *stream);
+int ldb_launch_inflate_resolve(const ldb_inflate_args &a, const ldb_launch_cfg &cfg, void *stream);
+u32 *ldb_inflate_resolve_counter(const ldb_inflate_args &a, const ldb_launch_cfg &cfg);
 size_t ldb_inflate_overflow_bytes_per_stream(void);
 int ldb_inflate_grid_blocks(const ldb_launch_cfg &cfg);
 size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg);

@@ -113,7 +113,7 @@ struct ldb_buf {
 };
 
 // kernel kinds for libdeflate_b200_kernel_time_ms()
-enum { LDB_K_CRC32 = 0, LDB_K_ADLER32 = 1, LDB_K_INFLATE = 2, LDB_K_VERIFY = 3, LDB_K_DEFLATE = 4, LDB_KERNEL_KINDS = 5 };
+enum { LDB_K_CRC32 = 0, LDB_K_ADLER32 = 1, LDB_K_INFLATE = 2, LDB_K_VERIFY = 3, LDB_K_DEFLATE = 4, LDB_K_RESOLVE = 5, LDB_KERNEL_KINDS = 6 };
 struct ldb_prof_rec {
 	cudaEvent_t a, b;
 	int kind;
@@ -125,6 +125,7 @@ struct libdeflate_b200_ctx {
 	ldb_launch_cfg cfg;
 	ldb_crc_tables *d_crc_tables;
 	ldb_buf inflate_scratch;	// device
+	ldb_buf token_scratch;		// device: token streams between the two inflate kernels
 	ldb_buf deflate_scratch;	// device
 	ldb_buf tmp;			// device: per-batch u32/size_t arrays
 	ldb_buf d_stage_in, d_stage_out;// device staging for host-buffer calls
@@ -243,6 +244,7 @@ extern "C" void libdeflate_b200_ctx_destroy(struct libdeflate_b200_ctx *ctx)
 	if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
 	cudaFree(ctx->d_crc_tables);
 	cudaFree(ctx->inflate_scratch.p);
+	cudaFree(ctx->token_scratch.p);
 	cudaFree(ctx->deflate_scratch.p);
 	cudaFree(ctx->tmp.p);
 	cudaFree(ctx->d_stage_in.p);
@@ -280,7 +282,7 @@ template <typename F> static int ldb_timed_launch(libdeflate_b200_ctx *ctx, int 
 extern "C" void libdeflate_b200_ctx_set_profiling(struct libdeflate_b200_ctx *ctx, int on) { ctx->profiling = on; }
 
 // Sum of device time (ms) and number of launches of one kernel kind since the last reset;
-// synchronises the stream.  kind: 0 crc32, 1 adler32, 2 inflate, 3 verify, 4 deflate.
+// synchronises the stream.  kind: 0 crc32, 1 adler32, 2 inflate (decode), 3 verify, 4 deflate, 5 inflate (resolve).
 extern "C" double libdeflate_b200_kernel_time_ms(struct libdeflate_b200_ctx *ctx, int kind, uint64_t *n_launches)
 {
 	cudaStreamSynchronize(ctx->stream);
@@ -361,6 +363,16 @@ extern "C" int libdeflate_b200_memcpy_d2h(struct libdeflate_b200_ctx *ctx, void 
 // ---------------------------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
+// host scratch that is released on every exit path (the CUDA error checks return early)
+struct host_scratch {
+	void *p;
+	explicit host_scratch(size_t n) : p(malloc(n)) {}
+	~host_scratch() { free(p); }
+	host_scratch(const host_scratch &) = delete;
+	host_scratch &operator=(const host_scratch &) = delete;
+};
+
+
 extern "C" int libdeflate_b200_crc32_batch(struct libdeflate_b200_ctx *ctx, const void *const *d_ptrs,
 					    const size_t *d_nbytes, const uint32_t *d_init,
 					    uint32_t *d_values, size_t n)
@@ -377,18 +389,37 @@ extern "C" int libdeflate_b200_adler32_batch(struct libdeflate_b200_ctx *ctx, co
 	return ldb_timed_launch(ctx, LDB_K_ADLER32, [&] { return ldb_launch_adler32(d_ptrs, d_nbytes, d_init, d_values, n, ctx->cfg, ctx->stream); });
 }
 
-extern "C" int libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
-						 const void *const *d_in_ptrs, const size_t *d_in_nbytes,
-						 void *const *d_out_ptrs, const size_t *d_out_avail,
-						 size_t *d_actual_in, size_t *d_actual_out,
-						 int32_t *d_results, size_t n)
+// Token scratch the two inflate kernels share is handed out in WAVES of consecutive chunks whose
+// slots fit the budget (default 8 GiB; LIBDEFLATE_B200_TOKEN_BUDGET_MB overrides).  The slot sizes
+// depend on in_nbytes / out_avail, which live in device memory: when the caller cannot give the
+// host copies (h_in_nbytes / h_out_avail, as the *_host entry points can), the prefix sums are
+// computed on the device and read back -- the one place where this call waits for the stream.
+static size_t ldb_token_budget(void)
+{
+	size_t mb = 8192;
+	if (const char *e = getenv("LIBDEFLATE_B200_TOKEN_BUDGET_MB")) {
+		long v = atol(e);
+		if (v > 0) mb = (size_t)v;
+	}
+	return mb << 20;
+}
+
+static int ldb_decompress_batch_impl(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
+				     const void *const *d_in_ptrs, const size_t *d_in_nbytes,
+				     void *const *d_out_ptrs, const size_t *d_out_avail,
+				     size_t *d_actual_in, size_t *d_actual_out,
+				     int32_t *d_results, size_t n,
+				     const size_t *h_in_nbytes, const size_t *h_out_avail)
 {
 	if (n == 0) return 0;
 	if (format < LDB_FMT_RAW || format > LDB_FMT_GZIP) return ldb_fail(cudaErrorInvalidValue, "format", __FILE__, __LINE__);
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
 	int rc = ldb_reserve_dev(ctx->inflate_scratch, ldb_inflate_scratch_bytes(ctx->cfg));
 	if (rc) return rc;
 	// tmp layout: actual_out scratch (size_t[n]) | trailer u32[n] | isize u32[n] | checksums u32[n]
-	size_t tmp_bytes = align_up(n * sizeof(size_t), 256) + 3 * align_up(n * sizeof(u32), 256);
+	//             | token counts u32[2n] | token slot offsets u64[n + 1]
+	size_t tmp_bytes = align_up(n * sizeof(size_t), 256) + 3 * align_up(n * sizeof(u32), 256) +
+			   align_up(2 * n * sizeof(u32), 256) + align_up((n + 1) * sizeof(u64), 256);
 	rc = ldb_reserve_dev(ctx->tmp, tmp_bytes);
 	if (rc) return rc;
 	u8 *t = (u8 *)ctx->tmp.p;
@@ -399,6 +430,31 @@ extern "C" int libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx,
 	u32 *isize = (u32 *)t;
 	t += align_up(n * sizeof(u32), 256);
 	u32 *sums = (u32 *)t;
+	t += align_up(n * sizeof(u32), 256);
+	u32 *tok_counts = (u32 *)t;
+	t += align_up(2 * n * sizeof(u32), 256);
+	u64 *d_tok_off = (u64 *)t;
+
+	// slot offsets, on both sides
+	host_scratch h_off_own((n + 1) * sizeof(u64));
+	u64 *h_off = (u64 *)h_off_own.p;
+	if (!h_off) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
+	if (h_in_nbytes && h_out_avail) {
+		u64 acc = 0;
+		for (size_t i = 0; i < n; i++) {
+			h_off[i] = acc;
+			acc += ldb_inflate_tok_cap(h_in_nbytes[i], h_out_avail[i]);
+		}
+		h_off[n] = acc;
+		LDB_CUDA_CHECK_RET(cudaMemcpyAsync(d_tok_off, h_off, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+		// h_off is pageable: the copy has been staged when the call returns
+	} else {
+		ctx->launches++;
+		rc = ldb_launch_inflate_caps(d_in_nbytes, d_out_avail, d_tok_off, n, ctx->stream);
+		if (rc) return rc;
+		LDB_CUDA_CHECK_RET(cudaMemcpyAsync(h_off, d_tok_off, (n + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+		LDB_CUDA_CHECK_RET(cudaStreamSynchronize(ctx->stream));
+	}
 
 	ldb_inflate_args a;
 	a.in_ptrs = d_in_ptrs;
@@ -411,11 +467,38 @@ extern "C" int libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx,
 	a.trailer_expect = trailer;
 	a.isize_expect = isize;
 	a.overflow_scratch = (u8 *)ctx->inflate_scratch.p;
+	a.tok_off = d_tok_off;
+	a.tok_counts = tok_counts;
 	a.n = n;
 	a.format = format;
 	a.flags = flags;
-	rc = ldb_timed_launch(ctx, LDB_K_INFLATE, [&] { return ldb_launch_inflate(a, ctx->cfg, ctx->stream); });
+
+	// waves
+	const u64 budget = ldb_token_budget();
+	u64 need = 0;
+	for (size_t i0 = 0; i0 < n;) {
+		size_t i1 = i0 + 1;
+		while (i1 < n && h_off[i1 + 1] - h_off[i0] <= budget) i1++;
+		if (h_off[i1] - h_off[i0] > need) need = h_off[i1] - h_off[i0];
+		i0 = i1;
+	}
+	rc = ldb_reserve_dev(ctx->token_scratch, (size_t)need + 256);
 	if (rc) return rc;
+	a.tok_base = (u8 *)ctx->token_scratch.p;
+	for (size_t i0 = 0; i0 < n;) {
+		size_t i1 = i0 + 1;
+		while (i1 < n && h_off[i1 + 1] - h_off[i0] <= budget) i1++;
+		a.first = i0;
+		a.count = i1 - i0;
+		a.tok_origin = h_off[i0];
+		rc = ldb_timed_launch(ctx, LDB_K_INFLATE, [&] { return ldb_launch_inflate(a, ctx->cfg, ctx->stream); });
+		if (rc) return rc;
+		rc = ldb_timed_launch(ctx, LDB_K_RESOLVE, [&] { return ldb_launch_inflate_resolve(a, ctx->cfg, ctx->stream); });
+		if (rc) return rc;
+		i0 = i1;
+	}
+	a.first = 0;
+	a.count = n;
 	if (format != LDB_FMT_RAW) {
 		// checksum of what was produced, then compare with the trailer
 		if (format == LDB_FMT_GZIP)
@@ -426,6 +509,16 @@ extern "C" int libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx,
 		rc = ldb_timed_launch(ctx, LDB_K_VERIFY, [&] { return ldb_launch_verify_trailer(a, sums, ctx->stream); });
 	}
 	return rc;
+}
+
+extern "C" int libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
+						 const void *const *d_in_ptrs, const size_t *d_in_nbytes,
+						 void *const *d_out_ptrs, const size_t *d_out_avail,
+						 size_t *d_actual_in, size_t *d_actual_out,
+						 int32_t *d_results, size_t n)
+{
+	return ldb_decompress_batch_impl(ctx, format, flags, d_in_ptrs, d_in_nbytes, d_out_ptrs, d_out_avail,
+					 d_actual_in, d_actual_out, d_results, n, nullptr, nullptr);
 }
 
 extern "C" int libdeflate_b200_compress_batch(struct libdeflate_b200_ctx *ctx, int format, int level,
@@ -507,15 +600,6 @@ struct staged_batch {
 	size_t *offsets;	// host, per chunk offset into slab (malloc'd, owned)
 	~staged_batch() { free(offsets); }
 };
-// host scratch that is released on every exit path (the CUDA error checks return early)
-struct host_scratch {
-	void *p;
-	explicit host_scratch(size_t n) : p(malloc(n)) {}
-	~host_scratch() { free(p); }
-	host_scratch(const host_scratch &) = delete;
-	host_scratch &operator=(const host_scratch &) = delete;
-};
-
 // Lays out n buffers of the given sizes in a device slab (16-byte aligned each, or
 // mirroring the host span when compact) and uploads pointer + size arrays.
 static int stage_layout(libdeflate_b200_ctx *ctx, ldb_buf &slab, const void *const *h_ptrs, const size_t *h_sizes,
@@ -667,8 +751,9 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 			if (ihi > ilo) LDB_CUDA_CHECK_RET(cudaMemcpyAsync(in_sb.d_base + imis + (ilo - isp.lo), ilo, (size_t)(ihi - ilo), cudaMemcpyHostToDevice, ctx->stream_h2d));
 			LDB_CUDA_CHECK_RET(cudaEventRecord(ev.in[k], ctx->stream_h2d));
 			LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream, ev.in[k], 0));
-			rc = libdeflate_b200_decompress_batch(ctx, format, flags, (const void *const *)in_sb.d_ptrs + i0, in_sb.d_sizes + i0,
-							      (void *const *)out_sb.d_ptrs + i0, out_sb.d_sizes + i0, d_ain + i0, d_aout + i0, d_res + i0, i1 - i0);
+			rc = ldb_decompress_batch_impl(ctx, format, flags, (const void *const *)in_sb.d_ptrs + i0, in_sb.d_sizes + i0,
+						       (void *const *)out_sb.d_ptrs + i0, out_sb.d_sizes + i0, d_ain + i0, d_aout + i0, d_res + i0, i1 - i0,
+						       h_in_nbytes + i0, h_out_avail + i0);
 			if (rc) break;
 			LDB_CUDA_CHECK_RET(cudaEventRecord(ev.done[k], ctx->stream));
 			LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream_d2h, ev.done[k], 0));
@@ -678,8 +763,8 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 		pipe_events_destroy(&ev);
 		out_copied = true;
 	} else if (!rc) {
-		rc = libdeflate_b200_decompress_batch(ctx, format, flags, (const void *const *)in_sb.d_ptrs, in_sb.d_sizes,
-						      (void *const *)out_sb.d_ptrs, out_sb.d_sizes, d_ain, d_aout, d_res, n);
+		rc = ldb_decompress_batch_impl(ctx, format, flags, (const void *const *)in_sb.d_ptrs, in_sb.d_sizes,
+					       (void *const *)out_sb.d_ptrs, out_sb.d_sizes, d_ain, d_aout, d_res, n, h_in_nbytes, h_out_avail);
 	}
 	u8 *hres = hparam + res_off;
 	if (!rc) rc = cudaMemcpyAsync(hres, dparam + res_off, res_bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "D2H results", __FILE__, __LINE__);
