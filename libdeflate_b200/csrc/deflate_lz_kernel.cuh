@@ -745,7 +745,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 	u16 *oparent = (u16 *)(sm + LZ_SM_R + 4608 + 128 + 512);
 	u16 *items = (u16 *)(sm + LZ_SM_ITEMS);				// precode items (<= 320 + slack)
 	// per-position results of the current pass live in this CTA's global scratch
-	u8 *gs = a.scratch + (size_t)blockIdx.x * LZ_GS_BYTES;
+	u8 *gs = a.scratch + 256 + (size_t)blockIdx.x * LZ_GS_BYTES;
 	u32 *res = (u32 *)(gs + LZ_GS_RES);	// per position: match length | (distance-1 | decision flag << 15) << 16
 	u32 *tokbuf = (u32 *)(gs + LZ_GS_TOK);
 	u32 *costg = (u32 *)(gs + LZ_GS_COST);
@@ -1880,20 +1880,19 @@ extern "C" __attribute__((visibility("default"))) void ldb_lz_timing_dump(void)
 }
 #endif
 
-size_t ldb_deflate_scratch_bytes(const ldb_launch_cfg &cfg)
+// work counter (first 256 bytes) + one scratch block per CTA that a batch of n chunks launches
+size_t ldb_deflate_scratch_bytes(const ldb_launch_cfg &cfg, size_t n)
 {
-	return (size_t)ldb_deflate_grid(cfg) * LZ_GS_BYTES + 256;
+	size_t ctas = n < (size_t)ldb_deflate_grid(cfg) ? n : (size_t)ldb_deflate_grid(cfg);
+	return 256 + ctas * LZ_GS_BYTES;
 }
 
 static int ldb_launch_deflate_lz(const ldb_deflate_args &a, const ldb_launch_cfg &cfg, void *stream)
 {
-	static bool attr_set = false;
-	if (!attr_set) {
-		LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_deflate_lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_BYTES));
-		attr_set = true;
-	}
+	// per device, cheap: set on every launch (contexts may live on different GPUs and threads)
+	LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_deflate_lz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_SM_BYTES));
 	ldb_deflate_args b = a;
-	b.work_counter = (u32 *)(a.scratch + (size_t)ldb_deflate_grid(cfg) * LZ_GS_BYTES);
+	b.work_counter = (u32 *)a.scratch;
 	LDB_CUDA_CHECK_RET(cudaMemsetAsync(b.work_counter, 0, sizeof(u32), (cudaStream_t)stream));
 	size_t blocks = a.n < (size_t)ldb_deflate_grid(cfg) ? a.n : (size_t)ldb_deflate_grid(cfg);
 	LDB_LAUNCH(ldb_deflate_lz_kernel, dim3((unsigned)blocks), dim3(LZ_THREADS), LZ_SM_BYTES, (cudaStream_t)stream, b);

@@ -693,7 +693,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 	u8 *sm = sm_cta + (threadIdx.x >> 5) * INF_SM_BYTES;
 	const u32 lane = threadIdx.x & 31;
 	const size_t gwarp = (size_t)blockIdx.x * INF_WPC + (threadIdx.x >> 5);	// global warp index
-	u16 *ovf = (u16 *)a.overflow_scratch + (gwarp * 32 + lane) * INF_OVF_ENTRIES;
+	u16 *ovf = (u16 *)(a.overflow_scratch + 256) + (gwarp * 32 + lane) * INF_OVF_ENTRIES;
 
 	inf_lane s;
 	s.state = ST_IDLE;
@@ -845,7 +845,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 			}
 			ol[0] = is_static ? 5u : (lane < hdist ? lens[scr_idx(hlit + lane, owner)] : 0);
 			__syncwarp();
-			u16 *ovf_owner = (u16 *)a.overflow_scratch + (gwarp * 32 + owner) * INF_OVF_ENTRIES;
+			u16 *ovf_owner = (u16 *)(a.overflow_scratch + 256) + (gwarp * 32 + owner) * INF_OVF_ENTRIES;
 			// offset code first, like the reference (decompress_template.h:331-332)
 			bool ok = inf_build_table<1, INF_OB, INF_OSUB_SM, INF_OSUB_CAP, false>(ol, sm, INF_SM_OTAB, ovf_owner + INF_OVF_L, owner, lane);
 			ok = ok && inf_build_table<9, INF_LB, INF_LSUB_SM, INF_LSUB_CAP, true>(ll, sm, INF_SM_LTAB, ovf_owner, owner, lane);
@@ -904,7 +904,7 @@ int ldb_launch_inflate(const ldb_inflate_args &a, const ldb_launch_cfg &cfg, voi
 	if (a.count == 0) return 0;
 	// the attribute is per device and cheap to set: every launch does it (a context may live on any GPU)
 	LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_WPC * INF_SM_BYTES));
-	u32 *counter = (u32 *)(a.overflow_scratch + (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream());
+	u32 *counter = (u32 *)a.overflow_scratch;	// the first 256 bytes of the scratch hold the two work counters
 	LDB_CUDA_CHECK_RET(cudaMemsetAsync(counter, 0, 2 * sizeof(u32), (cudaStream_t)stream));
 	size_t blocks = (a.count + 32 * INF_WPC - 1) / (32 * INF_WPC);
 	size_t cap = (size_t)ldb_inflate_grid_blocks(cfg) / INF_WPC;
@@ -917,7 +917,8 @@ int ldb_launch_inflate(const ldb_inflate_args &a, const ldb_launch_cfg &cfg, voi
 // work counter of the resolve kernel (zeroed by ldb_launch_inflate together with the decoder's)
 u32 *ldb_inflate_resolve_counter(const ldb_inflate_args &a, const ldb_launch_cfg &cfg)
 {
-	return (u32 *)(a.overflow_scratch + (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream()) + 1;
+	(void)cfg;
+	return (u32 *)a.overflow_scratch + 1;
 }
 
 // Number of WARPS (= groups of 32 concurrently decoded streams) the launch keeps resident.
@@ -929,9 +930,14 @@ int ldb_inflate_grid_blocks(const ldb_launch_cfg &cfg)
 	return cfg.num_sms * ctas_per_sm * INF_WPC;
 }
 
-size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg)
+// counters + overflow tables of the warps a batch of n chunks can occupy (a small batch -- the classic
+// single-buffer API is a batch of one -- needs a few KB, not the full-grid 0.57 GB)
+size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg, size_t n)
 {
-	return (size_t)ldb_inflate_grid_blocks(cfg) * 32 * ldb_inflate_overflow_bytes_per_stream() + 256;
+	size_t warps = (size_t)ldb_inflate_grid_blocks(cfg);
+	size_t ctas = (n + 32 * INF_WPC - 1) / (32 * INF_WPC);
+	if (ctas * INF_WPC < warps) warps = ctas * INF_WPC;
+	return 256 + warps * 32 * ldb_inflate_overflow_bytes_per_stream();
 }
 
 int ldb_launch_verify_trailer(const ldb_inflate_args &a, const u32 *d_checksums, void *stream)

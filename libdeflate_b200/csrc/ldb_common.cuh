@@ -130,7 +130,7 @@ int ldb_launch_inflate_resolve(const ldb_inflate_args &a, const ldb_launch_cfg &
 u32 *ldb_inflate_resolve_counter(const ldb_inflate_args &a, const ldb_launch_cfg &cfg);
 size_t ldb_inflate_overflow_bytes_per_stream(void);
 int ldb_inflate_grid_blocks(const ldb_launch_cfg &cfg);
-size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg);
+size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg, size_t n);
 int ldb_launch_verify_trailer(const ldb_inflate_args &a, const u32 *d_checksums, void *stream);
 
 struct ldb_deflate_args {
@@ -147,5 +147,5 @@ struct ldb_deflate_args {
 	int level;
 };
 int ldb_launch_deflate(const ldb_deflate_args &a, const ldb_launch_cfg &cfg, void *stream);
-size_t ldb_deflate_scratch_bytes(const ldb_launch_cfg &cfg);
+size_t ldb_deflate_scratch_bytes(const ldb_launch_cfg &cfg, size_t n);
 int ldb_deflate_grid(const ldb_launch_cfg &cfg);

@@ -349,11 +349,13 @@ extern "C" void *libdeflate_b200_pinned_malloc(size_t nbytes)
 extern "C" void libdeflate_b200_pinned_free(void *h_ptr) { cudaFreeHost(h_ptr); }
 extern "C" int libdeflate_b200_memcpy_h2d(struct libdeflate_b200_ctx *ctx, void *d_dst, const void *h_src, size_t nbytes)
 {
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
 	LDB_CUDA_CHECK_RET(cudaMemcpyAsync(d_dst, h_src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
 	return 0;
 }
 extern "C" int libdeflate_b200_memcpy_d2h(struct libdeflate_b200_ctx *ctx, void *h_dst, const void *d_src, size_t nbytes)
 {
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
 	LDB_CUDA_CHECK_RET(cudaMemcpyAsync(h_dst, d_src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
 	return 0;
 }
@@ -378,6 +380,7 @@ extern "C" int libdeflate_b200_crc32_batch(struct libdeflate_b200_ctx *ctx, cons
 					    uint32_t *d_values, size_t n)
 {
 	if (n == 0) return 0;
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
 	return ldb_timed_launch(ctx, LDB_K_CRC32, [&] { return ldb_launch_crc32(ctx->d_crc_tables, d_ptrs, d_nbytes, d_init, d_values, n, ctx->cfg, ctx->stream); });
 }
 
@@ -386,6 +389,7 @@ extern "C" int libdeflate_b200_adler32_batch(struct libdeflate_b200_ctx *ctx, co
 					      uint32_t *d_values, size_t n)
 {
 	if (n == 0) return 0;
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
 	return ldb_timed_launch(ctx, LDB_K_ADLER32, [&] { return ldb_launch_adler32(d_ptrs, d_nbytes, d_init, d_values, n, ctx->cfg, ctx->stream); });
 }
 
@@ -414,7 +418,7 @@ static int ldb_decompress_batch_impl(struct libdeflate_b200_ctx *ctx, int format
 	if (n == 0) return 0;
 	if (format < LDB_FMT_RAW || format > LDB_FMT_GZIP) return ldb_fail(cudaErrorInvalidValue, "format", __FILE__, __LINE__);
 	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
-	int rc = ldb_reserve_dev(ctx->inflate_scratch, ldb_inflate_scratch_bytes(ctx->cfg));
+	int rc = ldb_reserve_dev(ctx->inflate_scratch, ldb_inflate_scratch_bytes(ctx->cfg, n));
 	if (rc) return rc;
 	// tmp layout: actual_out scratch (size_t[n]) | trailer u32[n] | isize u32[n] | checksums u32[n]
 	//             | token counts u32[2n] | token slot offsets u64[n + 1]
@@ -530,7 +534,8 @@ extern "C" int libdeflate_b200_compress_batch(struct libdeflate_b200_ctx *ctx, i
 	if (format < LDB_FMT_RAW || format > LDB_FMT_GZIP) return ldb_fail(cudaErrorInvalidValue, "format", __FILE__, __LINE__);
 	if (level == -1) level = 6;
 	if (level < 0 || level > 12) return ldb_fail(cudaErrorInvalidValue, "level", __FILE__, __LINE__);
-	int rc = ldb_reserve_dev(ctx->deflate_scratch, ldb_deflate_scratch_bytes(ctx->cfg));
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
+	int rc = ldb_reserve_dev(ctx->deflate_scratch, ldb_deflate_scratch_bytes(ctx->cfg, n));
 	if (rc) return rc;
 	rc = ldb_reserve_dev(ctx->tmp, align_up(n * sizeof(u32), 256));
 	if (rc) return rc;
