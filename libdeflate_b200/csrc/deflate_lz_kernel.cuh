@@ -952,6 +952,7 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 					}
 					u32 fin = pb0 + e;
 					if (fin < ppend) fin = ppend;
+					__syncwarp();	// every lane has read parse_entry (racecheck: read/write by different lanes)
 					if (lane == 0) v->parse_entry = fin;
 				}
 				__syncthreads();

@@ -115,7 +115,9 @@ static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry")
 #define LE_SUB_FLAG  0xC000u
 #define OE_SUB_FLAG  0x8000u
 
-enum { ST_IDLE = 0, ST_HEADER = 1, ST_BUILD = 2, ST_STORED = 3, ST_DECODE = 4 };
+// ST_LIT: the next thing in the stream is a litlen symbol; ST_OFF: a length has been decoded, its
+// offset is next; ST_DONE: the stream has ended with s.verdict (finished in the service phase)
+enum { ST_IDLE = 0, ST_HEADER = 1, ST_BUILD = 2, ST_STORED = 3, ST_DONE = 4, ST_LIT = 5, ST_OFF = 6 };
 
 size_t ldb_inflate_overflow_bytes_per_stream(void) { return INF_OVF_ENTRIES * sizeof(u16); }
 
@@ -131,21 +133,24 @@ struct inf_lane {
 	u32 w0, w1, w2;
 	u32 bitpos;		// bits of w0 already consumed
 	// token output: literal bytes are gathered into aligned 4-byte words of the literal stream,
-	// records are written downwards from the end of the chunk's slot
+	// records are written downwards from the end of the chunk's slot.  The output position is
+	// n_lit + (bytes of all matches so far); kept as lit_limit = out_avail - match bytes, so that
+	// "no room for a literal" is n_lit == lit_limit.
 	u8 *lit;		// literal stream (16-byte aligned)
 	u32 *rec_end;		// one past the slot's last u32; record j lives at rec_end[-1 - j]
 	u32 n_lit;		// literal bytes emitted (the low two bits count the bytes pending in acc)
 	u32 n_rec;
-	u32 litrun;		// literals since the last record
-	u32 out_pos;		// bytes the stream has produced so far
+	u32 lit_mark;		// n_lit at the last record
+	u32 lit_limit;		// out_avail - bytes of all matches so far
 	u32 out_avail;
-	u32 acc;		// the (n_lit & 3) pending bytes of the current literal word
+	u32 acc;		// the (n_lit & 3) pending bytes of the current literal word, in its TOP bytes
 	// block state
 	u32 state;
+	u32 verdict;		// valid in ST_DONE
 	u32 is_final;
 	u32 hlit, hdist, is_static;
 	u32 stored_len, stored_src;
-	u32 pend_len;		// decoded match length whose offset has not been decoded yet
+	u32 pend_len;		// decoded match length whose offset has not been decoded yet (ST_OFF)
 	// bookkeeping
 	u32 chunk;		// chunk index
 	u32 hdr_bytes;		// wrapper header size
@@ -206,23 +211,26 @@ __device__ __forceinline__ u64 inf_bits_consumed(const inf_lane &s)
 	return (u64)s.wpos * 8 + s.bitpos - 8 * s.in_a0;
 }
 
+// P - 8n in 32-bit arithmetic; only meaningful near the end of the input (wpos + 8 > in_nal)
+__device__ __forceinline__ s32 inf_bits_past_end(const inf_lane &s)
+{
+	return 8 * (s32)(s.wpos - s.in_nal) + (s32)s.bitpos;
+}
+
 // ---- token output ---------------------------------------------------------------
+// a literal enters the accumulator from the top: after four of them the word is complete
 __device__ __forceinline__ void inf_put_byte(inf_lane &s, u32 b)
 {
-	s.acc |= b << (8 * (s.n_lit & 3));
+	s.acc = __funnelshift_r(s.acc, b, 8);
 	s.n_lit++;
-	s.litrun++;
-	s.out_pos++;
-	if ((s.n_lit & 3) == 0) {
-		*(u32 *)(s.lit + s.n_lit - 4) = s.acc;
-		s.acc = 0;
-	}
+	if ((s.n_lit & 3) == 0) *(u32 *)(s.lit + s.n_lit - 4) = s.acc;
 }
 
 // the pending literal bytes go to memory (the word's upper bytes are scratch: the slot has slack)
 __device__ __forceinline__ void inf_flush_pending(const inf_lane &s)
 {
-	if (s.n_lit & 3) *(u32 *)(s.lit + (s.n_lit & ~3u)) = s.acc;
+	u32 c = s.n_lit & 3;
+	if (c) *(u32 *)(s.lit + (s.n_lit & ~3u)) = s.acc >> (8 * (4 - c));
 }
 
 // after literal bytes were written behind our back (stored blocks): reload the pending bytes
@@ -230,7 +238,7 @@ __device__ __forceinline__ void inf_reload_pending(inf_lane &s)
 {
 	u32 c = s.n_lit & 3;
 	s.acc = 0;
-	if (c) s.acc = *(volatile u32 *)(s.lit + (s.n_lit & ~3u)) & ((1u << (8 * c)) - 1);
+	if (c) s.acc = *(volatile u32 *)(s.lit + (s.n_lit & ~3u)) << (8 * (4 - c));
 }
 
 __device__ __forceinline__ void inf_put_record(inf_lane &s, u32 r)
@@ -239,16 +247,20 @@ __device__ __forceinline__ void inf_put_record(inf_lane &s, u32 r)
 	*(s.rec_end - s.n_rec) = r;
 }
 
+// bytes the stream has produced so far
+__device__ __forceinline__ u32 inf_out_pos(const inf_lane &s) { return s.n_lit + (s.out_avail - s.lit_limit); }
+
 // a match of 'length' bytes at distance 'offset', preceded by the literals since the last record
 __device__ __forceinline__ void inf_put_match(inf_lane &s, u32 length, u32 offset)
 {
-	if (s.litrun > 255) {
-		inf_put_record(s, LDB_TOK_PURE_FLAG | s.litrun);
-		s.litrun = 0;
+	u32 litrun = s.n_lit - s.lit_mark;
+	if (litrun > 255) {
+		inf_put_record(s, LDB_TOK_PURE_FLAG | litrun);
+		litrun = 0;
 	}
-	inf_put_record(s, (s.litrun << 23) | ((length - 3) << 15) | (offset - 1));
-	s.litrun = 0;
-	s.out_pos += length;
+	inf_put_record(s, (litrun << 23) | ((length - 3) << 15) | (offset - 1));
+	s.lit_mark = s.n_lit;
+	s.lit_limit -= length;
 }
 
 // ---- wrapper headers ------------------------------------------------------------
@@ -403,7 +415,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 		u32 len = s.in[B] | ((u32)s.in[B + 1] << 8);
 		u32 nlen = s.in[B + 2] | ((u32)s.in[B + 3] << 8);
 		if (len != (nlen ^ 0xffffu)) return LDB_BAD_DATA;
-		if (len > s.out_avail - s.out_pos) return LDB_INSUFFICIENT_SPACE;
+		if (len > s.lit_limit - s.n_lit) return LDB_INSUFFICIENT_SPACE;
 		if (len > s.in_n - (B + 4)) return LDB_BAD_DATA;
 		s.stored_src = B + 4;	// source position of the raw bytes
 		s.stored_len = len;
@@ -599,18 +611,20 @@ __device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
 }
 
 // ---- decoding, split in two so that the warp can run several cheap litlen rounds (most
-// symbols are literals) before it pays for ONE expensive match round with many lanes in it --
+// symbols are literals) before it pays for ONE offset round with many lanes in it -----------
+// Both functions end the stream by moving to ST_DONE with a verdict; the bookkeeping of a finished
+// stream happens once per service phase, outside the hot loop.
 //
-// inf_decode_litlen: one litlen symbol.  Literal -> stored.  End of block -> state ST_HEADER.
-// Length -> s.pend_len set (> 0); the offset is decoded by inf_decode_offset.
-__device__ __forceinline__ int inf_decode_litlen(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
+// inf_decode_litlen: one litlen symbol.  Literal -> emitted.  End of block -> ST_HEADER, or ST_DONE
+// when the block was the final one.  Length -> ST_OFF with s.pend_len set.
+__device__ __forceinline__ void inf_decode_litlen(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
 {
 	const u16 *ltab = (const u16 *)(sm + INF_SM_LTAB);
 	u32 bits = inf_peek(s);
 	if (s.wpos + 8 > s.in_nal) {
 		// virtual zero bytes are (nearly) in play: P >= 8n+9 means the reference's refill
 		// over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
-		if (inf_bits_consumed(s) >= (u64)s.in_n * 8 + 9) return LDB_BAD_DATA;
+		if (inf_bits_past_end(s) >= 9) { s.verdict = LDB_BAD_DATA; s.state = ST_DONE; return; }
 	}
 	u32 e = ltab[tab_idx(bits & (INF_LMAIN - 1), lane)];
 	if (e >= LE_SUB_FLAG) {
@@ -622,18 +636,19 @@ __device__ __forceinline__ int inf_decode_litlen(inf_lane &s, const u8 *sm, cons
 		e = idx < INF_LSUB_SM ? ltab[tab_idx(INF_LMAIN + idx, lane)] : ovf[idx - INF_LSUB_SM];
 	}
 	u32 cl = e & 15;
-	bits >>= cl;
 	s.bitpos += cl;
 	if (e < 0x1000) {
-		if (s.out_pos == s.out_avail) return LDB_INSUFFICIENT_SPACE;
+		if (s.n_lit == s.lit_limit) { s.verdict = LDB_INSUFFICIENT_SPACE; s.state = ST_DONE; return; }
 		inf_put_byte(s, e >> 4);
-		return LDB_SUCCESS;
+		return;
 	}
 	if (e & LE_EOB_FLAG) {
-		s.state = ST_HEADER;	// caller turns this into "done" when is_final
-		return LDB_SUCCESS;
+		s.verdict = LDB_SUCCESS;
+		s.state = s.is_final ? ST_DONE : ST_HEADER;
+		return;
 	}
 	// length (Appendix A table, ref: deflate_decompress.c:576-587); 'bits' still holds >= 12 bits
+	bits >>= cl;
 	u32 slot = (e >> 4) & 31;
 	u32 length;
 	if (slot < 8) {
@@ -645,13 +660,13 @@ __device__ __forceinline__ int inf_decode_litlen(inf_lane &s, const u8 *sm, cons
 	} else {
 		length = 258;
 	}
-	if (length > s.out_avail - s.out_pos) return LDB_INSUFFICIENT_SPACE;
+	if (length > s.lit_limit - s.n_lit) { s.verdict = LDB_INSUFFICIENT_SPACE; s.state = ST_DONE; return; }
 	s.pend_len = length;
-	return LDB_SUCCESS;
+	s.state = ST_OFF;
 }
 
 // inf_decode_offset: the offset of the pending length; emits the match record.
-__device__ __forceinline__ int inf_decode_offset(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
+__device__ __forceinline__ void inf_decode_offset(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
 {
 	const u16 *otab = (const u16 *)(sm + INF_SM_OTAB);
 	u32 bits = inf_peek(s);
@@ -676,10 +691,9 @@ __device__ __forceinline__ int inf_decode_offset(inf_lane &s, const u8 *sm, cons
 		offset = 1 + ((2 + (oslot & 1)) << eb) + (bits & ((1u << eb) - 1));
 		s.bitpos += eb;
 	}
-	if (offset > s.out_pos) return LDB_BAD_DATA;
+	if (offset > inf_out_pos(s)) { s.verdict = LDB_BAD_DATA; s.state = ST_DONE; return; }
 	inf_put_match(s, s.pend_len, offset);
-	s.pend_len = 0;
-	return LDB_SUCCESS;
+	s.state = ST_LIT;
 }
 
 // ---- the decode kernel --------------------------------------------------------------
@@ -697,15 +711,18 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 
 	inf_lane s;
 	s.state = ST_IDLE;
+	s.verdict = LDB_SUCCESS;
 	s.chunk = 0xffffffffu;
 	s.in = nullptr; s.in_al = nullptr; s.in_a0 = 0; s.in_n = 0; s.in_nal = 0; s.wpos = 0; s.w0 = 0; s.w1 = 0; s.w2 = 0; s.bitpos = 0;
-	s.lit = nullptr; s.rec_end = nullptr; s.n_lit = 0; s.n_rec = 0; s.litrun = 0; s.out_pos = 0; s.out_avail = 0; s.acc = 0;
+	s.lit = nullptr; s.rec_end = nullptr; s.n_lit = 0; s.n_rec = 0; s.lit_mark = 0; s.lit_limit = 0; s.out_avail = 0; s.acc = 0;
 	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.pend_len = 0;
 	bool exhausted = false;
 
-	// finishes the lane's stream with 'verdict' and makes the lane idle
-	auto finish = [&](int verdict) {
+	// the bookkeeping of a stream that has ended (ST_DONE) with s.verdict; the lane becomes idle
+	auto finish = [&]() {
 		const size_t c = s.chunk;
+		int verdict = (int)s.verdict;
+		const u32 out_pos = inf_out_pos(s);
 		u32 footer = a.format == LDB_FMT_GZIP ? 8 : (a.format == LDB_FMT_ZLIB ? 4 : 0);
 		if (verdict == LDB_SUCCESS) {
 			u64 P = inf_bits_consumed(s);
@@ -713,8 +730,8 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 			else {
 				u32 used = (u32)((P + 7) >> 3);
 				if (a.actual_in) a.actual_in[c] = (size_t)s.hdr_bytes + used + footer;
-				a.actual_out[c] = s.out_pos;
-				if ((a.flags & 1u) && s.out_pos != s.out_avail) verdict = LDB_SHORT_OUTPUT;
+				a.actual_out[c] = out_pos;
+				if ((a.flags & 1u) && out_pos != s.out_avail) verdict = LDB_SHORT_OUTPUT;
 				else if (footer) {
 					const u8 *t = s.in + used;
 					if (a.format == LDB_FMT_GZIP) {
@@ -729,7 +746,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 		if (verdict == LDB_SUCCESS || verdict == LDB_SHORT_OUTPUT) {
 			// the whole stream decoded: hand its tokens to the resolve kernel
 			inf_flush_pending(s);
-			if (s.litrun) inf_put_record(s, LDB_TOK_PURE_FLAG | s.litrun);
+			if (s.n_lit != s.lit_mark) inf_put_record(s, LDB_TOK_PURE_FLAG | (s.n_lit - s.lit_mark));
 			a.tok_counts[2 * c] = s.n_rec;
 			a.tok_counts[2 * c + 1] = s.n_lit;
 		} else {
@@ -742,142 +759,140 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 	};
 
 	for (;;) {
-		// ---- service phase -------------------------------------------------
-		// (1) idle lanes fetch new chunks
-		u32 idle = __ballot_sync(LDB_FULL_MASK, s.state == ST_IDLE && !exhausted);
-		if (idle) {
-			u32 base = 0;
-			if (lane == (u32)(__ffs(idle) - 1)) base = atomicAdd(work_counter, (u32)__popc(idle));
-			base = __shfl_sync(LDB_FULL_MASK, base, __ffs(idle) - 1);
-			if (s.state == ST_IDLE && !exhausted) {
-				size_t c = (size_t)base + __popc(idle & ((1u << lane) - 1));
-				if (c >= a.count) {
-					exhausted = true;
-				} else {
-					c += a.first;
-					s.chunk = (u32)c;
-					const u8 *in = (const u8 *)a.in_ptrs[c];
-					size_t n = a.in_nbytes[c];
-					size_t oa = a.out_avail[c];
-					s.out_avail = oa > 0xfffffff0u ? 0xfffffff0u : (u32)oa;
-					s.out_pos = 0;
-					s.acc = 0;
-					s.pend_len = 0;
-					s.lit = a.tok_base + (a.tok_off[c] - a.tok_origin);
-					s.rec_end = (u32 *)(a.tok_base + (a.tok_off[c + 1] - a.tok_origin));
-					s.n_lit = 0;
-					s.n_rec = 0;
-					s.litrun = 0;
-					u32 footer;
-					u32 hdr = inf_parse_wrapper(in, n, a.format, &footer);
-					if (hdr == 0xffffffffu) {
-						a.actual_out[c] = 0;
-						a.tok_counts[2 * c] = 0;
-						a.tok_counts[2 * c + 1] = 0;
-						a.results[c] = LDB_BAD_DATA;
+		// ---- service phase: everything that is not symbol decoding.  Repeated (a few times) while
+		// lanes keep coming back to it, so that streams made of stored or tiny blocks do not crawl
+		// through it once per decode quantum.
+#pragma unroll 1
+		for (int rep = 0; rep < 4; rep++) {
+			// (0) streams that have ended
+			if (s.state == ST_DONE) finish();
+			// (1) idle lanes fetch new chunks
+			u32 idle = __ballot_sync(LDB_FULL_MASK, s.state == ST_IDLE && !exhausted);
+			if (idle) {
+				u32 base = 0;
+				if (lane == (u32)(__ffs(idle) - 1)) base = atomicAdd(work_counter, (u32)__popc(idle));
+				base = __shfl_sync(LDB_FULL_MASK, base, __ffs(idle) - 1);
+				if (s.state == ST_IDLE && !exhausted) {
+					size_t c = (size_t)base + __popc(idle & ((1u << lane) - 1));
+					if (c >= a.count) {
+						exhausted = true;
 					} else {
-						size_t dn = n - hdr - footer;
-						s.in = in + hdr;
-						s.in_n = dn > 0xfffffff0u ? 0xfffffff0u : (u32)dn;
-						s.in_a0 = (u32)(uintptr_t)s.in & 3;
-						s.in_al = s.in - s.in_a0;
-						s.in_nal = s.in_a0 + s.in_n;
-						s.hdr_bytes = hdr;
-						inf_bits_init(s, 0);
-						s.state = ST_HEADER;
+						c += a.first;
+						s.chunk = (u32)c;
+						const u8 *in = (const u8 *)a.in_ptrs[c];
+						size_t n = a.in_nbytes[c];
+						size_t oa = a.out_avail[c];
+						s.out_avail = oa > 0xfffffff0u ? 0xfffffff0u : (u32)oa;
+						s.lit_limit = s.out_avail;
+						s.acc = 0;
+						s.pend_len = 0;
+						s.lit = a.tok_base + (a.tok_off[c] - a.tok_origin);
+						s.rec_end = (u32 *)(a.tok_base + (a.tok_off[c + 1] - a.tok_origin));
+						s.n_lit = 0;
+						s.n_rec = 0;
+						s.lit_mark = 0;
+						u32 footer;
+						u32 hdr = inf_parse_wrapper(in, n, a.format, &footer);
+						if (hdr == 0xffffffffu) {
+							a.actual_out[c] = 0;
+							a.tok_counts[2 * c] = 0;
+							a.tok_counts[2 * c + 1] = 0;
+							a.results[c] = LDB_BAD_DATA;
+						} else {
+							size_t dn = n - hdr - footer;
+							s.in = in + hdr;
+							s.in_n = dn > 0xfffffff0u ? 0xfffffff0u : (u32)dn;
+							s.in_a0 = (u32)(uintptr_t)s.in & 3;
+							s.in_al = s.in - s.in_a0;
+							s.in_nal = s.in_a0 + s.in_n;
+							s.hdr_bytes = hdr;
+							inf_bits_init(s, 0);
+							s.state = ST_HEADER;
+						}
 					}
 				}
 			}
-		}
-		if (__all_sync(LDB_FULL_MASK, s.state == ST_IDLE)) {
-			if (__all_sync(LDB_FULL_MASK, exhausted)) break;
-			continue;	// e.g. every fetched chunk had a bad wrapper header
-		}
 
-		// (2) block headers, parsed by their own lanes
-		if (s.state == ST_HEADER) {
-			int v = inf_parse_block_header(s, sm, lane);
-			if (v != LDB_SUCCESS) finish(v);
-		}
-		__syncwarp();
-
-		// (3) stored blocks: their bytes are literals; warp-wide coalesced copy into the literal
-		// stream, one lane's block at a time
-		u32 stored = __ballot_sync(LDB_FULL_MASK, s.state == ST_STORED);
-		while (stored) {
-			u32 owner = __ffs(stored) - 1;
-			stored &= stored - 1;
-			// the owner's pending literal bytes must be in memory first
-			if (lane == owner) inf_flush_pending(s);
-			__syncwarp();
-			const u8 *src = (const u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.in + s.stored_src), owner);
-			u8 *dst = (u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.lit + s.n_lit), owner);
-			u32 len = __shfl_sync(LDB_FULL_MASK, s.stored_len, owner);
-			for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
-			__syncwarp();
-			if (lane == owner) {
-				s.out_pos += len;
-				s.n_lit += len;
-				s.litrun += len;
-				inf_reload_pending(s);
-				u32 next = s.stored_src + len;
-				inf_bits_init(s, next);	// P = 8 * next exactly
-				if (s.is_final) finish(LDB_SUCCESS);
-				else s.state = ST_HEADER;	// parsed in the next service phase
+			// (2) block headers, parsed by their own lanes
+			if (s.state == ST_HEADER) {
+				int v = inf_parse_block_header(s, sm, lane);
+				if (v != LDB_SUCCESS) { s.verdict = (u32)v; s.state = ST_DONE; }
 			}
-		}
+			__syncwarp();
 
-		// (4) table construction, one lane's tables at a time, whole warp
-		u32 build = __ballot_sync(LDB_FULL_MASK, s.state == ST_BUILD);
-		while (build) {
-			u32 owner = __ffs(build) - 1;
-			build &= build - 1;
-			u32 hlit = __shfl_sync(LDB_FULL_MASK, s.hlit, owner);
-			u32 hdist = __shfl_sync(LDB_FULL_MASK, s.hdist, owner);
-			u32 is_static = __shfl_sync(LDB_FULL_MASK, s.is_static, owner);
-			const u8 *lens = sm + INF_SM_LTAB;
-			u32 ll[9], ol[1];
+			// (3) stored blocks: their bytes are literals; warp-wide coalesced copy into the literal
+			// stream, one lane's block at a time
+			u32 stored = __ballot_sync(LDB_FULL_MASK, s.state == ST_STORED);
+			while (stored) {
+				u32 owner = __ffs(stored) - 1;
+				stored &= stored - 1;
+				// the owner's pending literal bytes must be in memory first
+				if (lane == owner) inf_flush_pending(s);
+				__syncwarp();
+				const u8 *src = (const u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.in + s.stored_src), owner);
+				u8 *dst = (u8 *)__shfl_sync(LDB_FULL_MASK, (u64)(uintptr_t)(s.lit + s.n_lit), owner);
+				u32 len = __shfl_sync(LDB_FULL_MASK, s.stored_len, owner);
+				for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
+				__syncwarp();
+				if (lane == owner) {
+					s.n_lit += len;
+					inf_reload_pending(s);
+					u32 next = s.stored_src + len;
+					inf_bits_init(s, next);	// P = 8 * next exactly
+					if (s.is_final) { s.verdict = LDB_SUCCESS; s.state = ST_DONE; }
+					else s.state = ST_HEADER;	// parsed in the next repetition
+				}
+			}
+
+			// (4) table construction, one lane's tables at a time, whole warp
+			u32 build = __ballot_sync(LDB_FULL_MASK, s.state == ST_BUILD);
+			while (build) {
+				u32 owner = __ffs(build) - 1;
+				build &= build - 1;
+				u32 hlit = __shfl_sync(LDB_FULL_MASK, s.hlit, owner);
+				u32 hdist = __shfl_sync(LDB_FULL_MASK, s.hdist, owner);
+				u32 is_static = __shfl_sync(LDB_FULL_MASK, s.is_static, owner);
+				const u8 *lens = sm + INF_SM_LTAB;
+				u32 ll[9], ol[1];
 #pragma unroll
-			for (int r = 0; r < 9; r++) {
-				u32 sym = r * 32 + lane;
-				ll[r] = is_static ? inf_static_litlen_len(sym)
-						  : (sym < hlit ? lens[scr_idx(sym, owner)] : 0);
+				for (int r = 0; r < 9; r++) {
+					u32 sym = r * 32 + lane;
+					ll[r] = is_static ? inf_static_litlen_len(sym)
+							  : (sym < hlit ? lens[scr_idx(sym, owner)] : 0);
+				}
+				ol[0] = is_static ? 5u : (lane < hdist ? lens[scr_idx(hlit + lane, owner)] : 0);
+				__syncwarp();
+				u16 *ovf_owner = (u16 *)(a.overflow_scratch + 256) + (gwarp * 32 + owner) * INF_OVF_ENTRIES;
+				// offset code first, like the reference (decompress_template.h:331-332)
+				bool ok = inf_build_table<1, INF_OB, INF_OSUB_SM, INF_OSUB_CAP, false>(ol, sm, INF_SM_OTAB, ovf_owner + INF_OVF_L, owner, lane);
+				ok = ok && inf_build_table<9, INF_LB, INF_LSUB_SM, INF_LSUB_CAP, true>(ll, sm, INF_SM_LTAB, ovf_owner, owner, lane);
+				__threadfence_block();
+				if (lane == owner) {
+					if (!ok) { s.verdict = LDB_BAD_DATA; s.state = ST_DONE; }
+					else s.state = ST_LIT;
+				}
 			}
-			ol[0] = is_static ? 5u : (lane < hdist ? lens[scr_idx(hlit + lane, owner)] : 0);
 			__syncwarp();
-			u16 *ovf_owner = (u16 *)(a.overflow_scratch + 256) + (gwarp * 32 + owner) * INF_OVF_ENTRIES;
-			// offset code first, like the reference (decompress_template.h:331-332)
-			bool ok = inf_build_table<1, INF_OB, INF_OSUB_SM, INF_OSUB_CAP, false>(ol, sm, INF_SM_OTAB, ovf_owner + INF_OVF_L, owner, lane);
-			ok = ok && inf_build_table<9, INF_LB, INF_LSUB_SM, INF_LSUB_CAP, true>(ll, sm, INF_SM_LTAB, ovf_owner, owner, lane);
-			__threadfence_block();
-			if (lane == owner) {
-				if (!ok) finish(LDB_BAD_DATA);
-				else s.state = ST_DECODE;
-			}
+			// again if a lane is back at a header, has ended, or idles while chunks are left
+			if (!__any_sync(LDB_FULL_MASK, s.state == ST_HEADER || s.state == ST_DONE || (s.state == ST_IDLE && !exhausted))) break;
 		}
-		__syncwarp();
+		if (__all_sync(LDB_FULL_MASK, s.state == ST_IDLE && exhausted)) break;
 
 		// ---- decode phase ----------------------------------------------------
+#pragma unroll 1
 		for (int it = 0; it < INF_QUANTUM; it++) {
 			// litlen rounds: lanes keep decoding literals until they hit a length (or the end
-			// of their block); stops early once most lanes wait for the match round
+			// of their block); stops early once most lanes wait for the offset round
 #pragma unroll 1
 			for (int r = 0; r < INF_LIT_ROUNDS; r++) {
-				if (s.state == ST_DECODE && s.pend_len == 0) {
-					int v = inf_decode_litlen(s, sm, ovf, lane);
-					if (v != LDB_SUCCESS) finish(v);
-					else if (s.state == ST_HEADER && s.is_final) finish(LDB_SUCCESS);
-				}
+				if (s.state == ST_LIT) inf_decode_litlen(s, sm, ovf, lane);
 				if (r + 1 < INF_LIT_ROUNDS &&
-				    __popc(__ballot_sync(LDB_FULL_MASK, s.state == ST_DECODE && s.pend_len == 0)) < INF_LIT_MIN_LANES)
+				    __popc(__ballot_sync(LDB_FULL_MASK, s.state == ST_LIT)) < INF_LIT_MIN_LANES)
 					break;
 			}
-			// match round: the offsets of the pending lengths, one record each
-			if (s.state == ST_DECODE && s.pend_len) {
-				int v = inf_decode_offset(s, sm, ovf, lane);
-				if (v != LDB_SUCCESS) finish(v);
-			}
-			if ((it & 15) == 15 && !__any_sync(LDB_FULL_MASK, s.state == ST_DECODE)) break;
+			// offset round: the offsets of the pending lengths, one record each
+			if (s.state == ST_OFF) inf_decode_offset(s, sm, ovf, lane);
+			if ((it & 15) == 15 && !__any_sync(LDB_FULL_MASK, s.state >= ST_LIT)) break;
 		}
 		__syncwarp();
 	}

@@ -6,41 +6,38 @@
 // forward byte-by-byte overlap semantics) -- from the chunk's token stream: packed literal
 // bytes + 4-byte {literal run, length, offset} records (format: ldb_common.cuh).
 //
-// B200 mapping -- one 256-thread CTA per chunk, three CTAs per SM:
-//   * the output lives in a 64 KiB shared-memory RING (index = position mod 65536, shifted so
-//     that 16-byte rows of the ring are 16-byte rows of the destination): the 32 KiB LZ77
-//     window never leaves the SM and never touches L2/HBM; finished bytes leave as coalesced
-//     16-byte rows, the only global stores of the kernel;
-//   * records are taken 256 at a time (one per thread); a CTA-wide prefix sum of
-//     {literals, literals + length} gives every thread its literal source and its destination;
-//   * literals are placed at once; a match whose source lies wholly before the block is copied
-//     at once (all of those are independent of each other); the others set "pending" bits over
-//     their destination range in a bitmap and are resolved in rounds: a match is ready when no
-//     byte of its source is pending -- exact dependency tracking, so the number of rounds is the
-//     depth of the dependency chains inside one block, not the number of matches;
-//   * a copy moves up to 16 bytes per step (aligned word loads, funnel shifts, word stores);
-//     an overlapping match (offset < length) doubles its effective offset after every period, so
-//     a run of 258 equal bytes takes log2 steps, not 258.
+// B200 mapping -- ONE WARP per chunk, six single-warp CTAs per SM, no block barriers:
+//   * LZ77 text has dependency chains hundreds of matches deep (every occurrence of a frequent
+//     word copies from the previous one), so the chunk is walked in order, 32 records (one per
+//     lane) at a time, and what counts is the latency of one dependent step and how many chunks
+//     an SM holds.  Shared memory per chunk: the 32 KiB window as a ring (committed bytes only)
+//     + a 4 KiB staging ring in which the current group is assembled = 36 KiB, 6 chunks per SM;
+//     the window never touches L2/HBM;
+//   * per group: two warp prefix sums ({literals}, {literals + length}) give every lane its
+//     literal source and its destination; all literal runs and all matches whose source lies in
+//     the window ("far": ~90 % of them) are copied by their own lanes at once, 16 bytes per step
+//     (aligned word loads, funnel shifts, word stores); the few matches that read bytes of the
+//     group itself are then done one after the other by the WHOLE warp, a byte per lane (the
+//     byte-by-byte overlap rule becomes index arithmetic: byte k comes from k mod offset);
+//   * finished 16-byte rows go staging -> window ring and staging -> global in the same pass:
+//     coalesced 16-byte stores are the only global stores of the kernel.
+// (A block-parallel version with exact dependency tracking in rounds was measured first: 232 K
+// warp instructions per chunk, ~50 rounds per 256 records on Zipf text -- profiles/r02_inflate_a.md.)
 //
 // Algorithmic HBM bytes per chunk: actual_out written once (+ the token stream read once, which
 // is the price of the two-kernel split; see inflate_kernel.cu).
 #include "ldb_common.cuh"
 
-#define RES_THREADS 256
-#define RES_WARPS   (RES_THREADS / 32)
-#define RES_RING    65536u
-#define RES_MASK    (RES_RING - 1)
-#define RES_SPAN    16384u	// most output bytes one block of records may cover
-#define RES_FLUSH   8192u	// finished bytes that trigger a write-out
-#define RES_LIT_FAST 8u		// literal runs up to this are placed by the owning thread
-
-// shared memory layout
-#define RES_SM_RING  0
-#define RES_SM_PEND  (RES_SM_RING + RES_RING)			// u32[RES_SPAN / 32]
-#define RES_SM_LIST  (RES_SM_PEND + RES_SPAN / 8)		// u32[3 * RES_THREADS]: {dst, src, n}
-#define RES_SM_WSUM  (RES_SM_LIST + 12 * RES_THREADS)		// u32[2 * RES_WARPS]
-#define RES_SM_MISC  (RES_SM_WSUM + 8 * RES_WARPS)		// u32[8]
-#define RES_SM_BYTES (RES_SM_MISC + 32)
+#define RES_WIN     32768u	// window ring: committed bytes, position q lives at q % 32768
+#define RES_WMASK   (RES_WIN - 1)
+#define RES_STG     4096u	// staging ring: the group being assembled, position q at q % 4096
+#define RES_SMASK   (RES_STG - 1)
+#define RES_SPAN    2048u	// most output bytes one group of records may cover
+#define RES_LIT_FAST 16u	// literal runs up to this are placed by the owning lane in one step
+#define RES_SM_BYTES (RES_WIN + RES_STG)
+#ifndef RES_PER_SM
+#define RES_PER_SM  6
+#endif
 
 // the scratch slot of a chunk: what the decoder can emit is bounded both by the output room
 // (a record stands for >= 3 bytes or for up to 2^31 literals) and by the input (a literal takes
@@ -92,119 +89,105 @@ int ldb_launch_inflate_caps(const size_t *d_in_nbytes, const size_t *d_out_avail
 	return 0;
 }
 
-// ---- pending bitmap (bit i = output byte P + i is not final yet) --------------------------------
-__device__ __forceinline__ void res_bits_set(u32 *bm, u32 lo, u32 hi)	// [lo, hi), hi > lo
+// ---- copies ----------------------------------------------------------------------------------------
+// Stores the first m (<= 16) bytes of the little-endian words v0..v3 at staging position qd:
+// single bytes up to the next word boundary, whole words, single bytes again.  Only bytes
+// [qd, qd + m) are written, so neighbouring lanes never touch each other's bytes.
+__device__ __forceinline__ void res_store16(u8 *stg, u32 qd, u32 m, u32 v0, u32 v1, u32 v2, u32 v3)
 {
-	u32 wl = lo >> 5, wh = (hi - 1) >> 5;
-	u32 ml = 0xffffffffu << (lo & 31), mh = 0xffffffffu >> (31 - ((hi - 1) & 31));
-	if (wl == wh) {
-		atomicOr(&bm[wl], ml & mh);
-	} else {
-		atomicOr(&bm[wl], ml);
-		for (u32 w = wl + 1; w < wh; w++) atomicOr(&bm[w], 0xffffffffu);
-		atomicOr(&bm[wh], mh);
-	}
-}
-__device__ __forceinline__ void res_bits_clear(u32 *bm, u32 lo, u32 hi)
-{
-	u32 wl = lo >> 5, wh = (hi - 1) >> 5;
-	u32 ml = 0xffffffffu << (lo & 31), mh = 0xffffffffu >> (31 - ((hi - 1) & 31));
-	if (wl == wh) {
-		atomicAnd(&bm[wl], ~(ml & mh));
-	} else {
-		atomicAnd(&bm[wl], ~ml);
-		for (u32 w = wl + 1; w < wh; w++) atomicAnd(&bm[w], 0u);
-		atomicAnd(&bm[wh], ~mh);
-	}
-}
-__device__ __forceinline__ bool res_bits_any(const u32 *bm, u32 lo, u32 hi)
-{
-	const volatile u32 *b = bm;
-	u32 wl = lo >> 5, wh = (hi - 1) >> 5;
-	u32 ml = 0xffffffffu << (lo & 31), mh = 0xffffffffu >> (31 - ((hi - 1) & 31));
-	if (wl == wh) return (b[wl] & ml & mh) != 0;
-	u32 acc = b[wl] & ml;
-	for (u32 w = wl + 1; w < wh; w++) acc |= b[w];
-	acc |= b[wh] & mh;
-	return acc != 0;
-}
-
-// ---- copies inside the ring --------------------------------------------------------------------
-// m <= 16 bytes from ring position qs to qd; the two ranges do not overlap.
-__device__ __forceinline__ void res_copy_piece(u8 *ring, u32 qd, u32 qs, u32 m)
-{
-	const u32 *r32 = (const u32 *)ring;
-	const u32 sa = qs & ~3u, ssh = 8 * (qs & 3);
-	const u32 need = (qs & 3) + m;		// source bytes counted from the aligned start
-	u32 w0 = r32[(sa & RES_MASK) >> 2], w1 = 0, w2 = 0, w3 = 0, w4 = 0;
-	if (need > 4) w1 = r32[((sa + 4) & RES_MASK) >> 2];
-	if (need > 8) w2 = r32[((sa + 8) & RES_MASK) >> 2];
-	if (need > 12) w3 = r32[((sa + 12) & RES_MASK) >> 2];
-	if (need > 16) w4 = r32[((sa + 16) & RES_MASK) >> 2];
-	u32 v0 = __funnelshift_r(w0, w1, ssh), v1 = __funnelshift_r(w1, w2, ssh);
-	u32 v2 = __funnelshift_r(w2, w3, ssh), v3 = __funnelshift_r(w3, w4, ssh);
-	// head: single bytes up to the next word boundary of the destination
 	u32 h = (4 - (qd & 3)) & 3;
 	if (h > m) h = m;
-	if (h > 0) ring[qd & RES_MASK] = (u8)v0;
-	if (h > 1) ring[(qd + 1) & RES_MASK] = (u8)(v0 >> 8);
-	if (h > 2) ring[(qd + 2) & RES_MASK] = (u8)(v0 >> 16);
-	// body: whole words, re-aligned to the destination
+	if (h > 0) stg[qd & RES_SMASK] = (u8)v0;
+	if (h > 1) stg[(qd + 1) & RES_SMASK] = (u8)(v0 >> 8);
+	if (h > 2) stg[(qd + 2) & RES_SMASK] = (u8)(v0 >> 16);
 	const u32 hsh = 8 * h;
 	u32 u0 = __funnelshift_r(v0, v1, hsh), u1 = __funnelshift_r(v1, v2, hsh);
 	u32 u2 = __funnelshift_r(v2, v3, hsh), u3 = v3 >> hsh;
-	u32 *d32 = (u32 *)ring;
+	u32 *d32 = (u32 *)stg;
 	const u32 qa = qd + h, rem = m - h, nw = rem >> 2;
-	if (nw > 0) d32[(qa & RES_MASK) >> 2] = u0;
-	if (nw > 1) d32[((qa + 4) & RES_MASK) >> 2] = u1;
-	if (nw > 2) d32[((qa + 8) & RES_MASK) >> 2] = u2;
-	if (nw > 3) d32[((qa + 12) & RES_MASK) >> 2] = u3;
-	// tail: the last rem & 3 bytes
+	if (nw > 0) d32[(qa & RES_SMASK) >> 2] = u0;
+	if (nw > 1) d32[((qa + 4) & RES_SMASK) >> 2] = u1;
+	if (nw > 2) d32[((qa + 8) & RES_SMASK) >> 2] = u2;
+	if (nw > 3) d32[((qa + 12) & RES_SMASK) >> 2] = u3;
 	const u32 t = rem & 3;
 	if (t) {
 		u32 tw = nw == 0 ? u0 : (nw == 1 ? u1 : (nw == 2 ? u2 : u3));
 		const u32 qt = qa + 4 * nw;
-		ring[qt & RES_MASK] = (u8)tw;
-		if (t > 1) ring[(qt + 1) & RES_MASK] = (u8)(tw >> 8);
-		if (t > 2) ring[(qt + 2) & RES_MASK] = (u8)(tw >> 16);
+		stg[qt & RES_SMASK] = (u8)tw;
+		if (t > 1) stg[(qt + 1) & RES_SMASK] = (u8)(tw >> 8);
+		if (t > 2) stg[(qt + 2) & RES_SMASK] = (u8)(tw >> 16);
 	}
 }
 
-// n bytes to qd from 'off' bytes back, with the byte-by-byte forward semantics of a DEFLATE
-// match (the source may run into the destination).  After each full period the effective
-// offset doubles: the bytes just written repeat the pattern.
-__device__ __forceinline__ void res_copy_match(u8 *ring, u32 qd, u32 off, u32 n)
+// m <= 16 bytes from window position qs (committed bytes) to staging position qd
+__device__ __forceinline__ void res_copy_piece(const u8 *win, u8 *stg, u32 qd, u32 qs, u32 m)
 {
-	u32 eff = off;
-	while (n) {
-		u32 m = n < 16 ? n : 16;
-		if (m > eff) m = eff;
-		res_copy_piece(ring, qd, qd - eff, m);
-		qd += m;
-		n -= m;
-		if (eff < 16) eff += eff;
+	const u32 *r32 = (const u32 *)win;
+	const u32 sa = qs & ~3u, ssh = 8 * (qs & 3);
+	const u32 need = (qs & 3) + m;		// source bytes counted from the aligned start
+	u32 w0 = r32[(sa & RES_WMASK) >> 2], w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+	if (need > 4) w1 = r32[((sa + 4) & RES_WMASK) >> 2];
+	if (need > 8) w2 = r32[((sa + 8) & RES_WMASK) >> 2];
+	if (need > 12) w3 = r32[((sa + 12) & RES_WMASK) >> 2];
+	if (need > 16) w4 = r32[((sa + 16) & RES_WMASK) >> 2];
+	res_store16(stg, qd, m, __funnelshift_r(w0, w1, ssh), __funnelshift_r(w1, w2, ssh),
+		    __funnelshift_r(w2, w3, ssh), __funnelshift_r(w3, w4, ssh));
+}
+
+// m <= 16 literal bytes from global memory (aligned 4-byte loads; the token slot has slack on
+// both sides of the literal range) to staging position qd
+__device__ __forceinline__ void res_lit_piece(const u8 *src, u8 *stg, u32 qd, u32 m)
+{
+	const u32 mis = (u32)(uintptr_t)src & 3, ssh = 8 * mis;
+	const u32 *A = (const u32 *)(src - mis);
+	const u32 need = mis + m;
+	u32 w0 = __ldg(A), w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+	if (need > 4) w1 = __ldg(A + 1);
+	if (need > 8) w2 = __ldg(A + 2);
+	if (need > 12) w3 = __ldg(A + 3);
+	if (need > 16) w4 = __ldg(A + 4);
+	res_store16(stg, qd, m, __funnelshift_r(w0, w1, ssh), __funnelshift_r(w1, w2, ssh),
+		    __funnelshift_r(w2, w3, ssh), __funnelshift_r(w3, w4, ssh));
+}
+
+// One match done by the whole warp, a byte per lane: the source may lie in the window (< B), in
+// the staging ring, or run into its own destination (offset < length).
+__device__ __forceinline__ void res_copy_coop(const u8 *win, u8 *stg, u32 B, u32 qd, u32 off, u32 n, u32 lane)
+{
+	const u32 s0 = qd - off;
+	if (off >= n || off >= 32) {
+		// an iteration reads nothing that the same iteration writes (32 consecutive bytes, offset >= 32)
+		for (u32 k = lane; k - lane < n; k += 32) {
+			if (k < n) {
+				u32 s = s0 + k;
+				u8 b = s < B ? win[s & RES_WMASK] : stg[s & RES_SMASK];
+				stg[(qd + k) & RES_SMASK] = b;
+			}
+			__syncwarp();
+		}
+	} else {
+		// periodic: byte k repeats byte k mod offset of the offset bytes before the destination
+		for (u32 k = lane; k < n; k += 32) {
+			u32 s = s0 + k % off;
+			u8 b = s < B ? win[s & RES_WMASK] : stg[s & RES_SMASK];
+			stg[(qd + k) & RES_SMASK] = b;
+		}
 	}
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RES_THREADS, 3)
+__global__ void __launch_bounds__(32)
 ldb_inflate_resolve_kernel(ldb_inflate_args a, u32 *work_counter)
 {
 	LDB_DYN_SMEM(sm);
-	u8 *ring = sm + RES_SM_RING;
-	u32 *pend = (u32 *)(sm + RES_SM_PEND);
-	u32 *list = (u32 *)(sm + RES_SM_LIST);
-	u32 *wsum = (u32 *)(sm + RES_SM_WSUM);
-	volatile u32 *misc = (volatile u32 *)(sm + RES_SM_MISC);	// 0 chunk, 1 list count, 2 first lits, 3 P', 4 L'
-	const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-	for (u32 i = tid; i < RES_SPAN / 32; i += RES_THREADS) pend[i] = 0;
+	u8 *win = sm;
+	u8 *stg = sm + RES_WIN;
+	const u32 lane = threadIdx.x;
 
 	for (;;) {
-		__syncthreads();	// the previous chunk's write-out has left the ring
-		if (tid == 0) misc[0] = atomicAdd(work_counter, 1u);
-		__syncthreads();
-		const size_t idx = misc[0];
+		u32 idx = 0;
+		if (lane == 0) idx = atomicAdd(work_counter, 1u);
+		idx = __shfl_sync(LDB_FULL_MASK, idx, 0);
 		if (idx >= a.count) break;
 		const size_t c = a.first + idx;
 		const u32 n_rec = a.tok_counts[2 * c];
@@ -212,132 +195,112 @@ ldb_inflate_resolve_kernel(ldb_inflate_args a, u32 *work_counter)
 		const u8 *lit = a.tok_base + (a.tok_off[c] - a.tok_origin);
 		const u32 *rec_end = (const u32 *)(a.tok_base + (a.tok_off[c + 1] - a.tok_origin));
 		u8 *const out = (u8 *)a.out_ptrs[c];
-		// shifted coordinates: q = output position + a0, so that q % 16 is the alignment phase of
-		// the destination and the ring index q % 65536 keeps 16-byte rows together
+		// shifted coordinates: q = output position + a0, so that q % 16 is the alignment phase of the
+		// destination: 16-byte rows of the two rings are 16-byte rows of global memory
 		const u32 a0 = (u32)(uintptr_t)out & 15;
 		u8 *const gbase = out - a0;
-		u32 P = a0;		// where the next block of records starts writing
+		u32 P = a0;		// where the next group starts writing
+		u32 B = 0;		// rows below B (a multiple of 16) are committed: in the window and in 'out'
 		u32 L = 0;		// literal bytes consumed
-		u32 flushed = a0;	// everything below has been written to 'out'
-		u32 r0 = 0;		// first record of the next block
+		u32 r0 = 0;		// first record of the next group
 		u32 big_rem = 0;	// what is left of a literal run longer than RES_SPAN
+		__syncwarp();		// the previous chunk's commit has left the rings
 
-		// write-out of ring bytes [flushed, upto): 16-byte rows, single bytes at ragged ends
-		auto write_out = [&](u32 upto) {
-			if (upto <= flushed) return;
-			u32 lo16 = (flushed + 15) & ~15u, hi16 = upto & ~15u;
-			if (lo16 >= hi16) {
-				for (u32 q = flushed + tid; q < upto; q += RES_THREADS) gbase[q] = ring[q & RES_MASK];
-			} else {
-				for (u32 q = flushed + tid; q < lo16; q += RES_THREADS) gbase[q] = ring[q & RES_MASK];
-				for (u32 q = lo16 + 16 * tid; q < hi16; q += 16 * RES_THREADS)
-					*(uint4 *)(gbase + q) = *(const uint4 *)(ring + (q & RES_MASK));
-				for (u32 q = hi16 + tid; q < upto; q += RES_THREADS) gbase[q] = ring[q & RES_MASK];
+		// staging rows [B, floor16(P)) -> window ring + global; with 'final' also the ragged tail
+		auto commit = [&](bool final) {
+			const u32 hi16 = P & ~15u;
+			for (u32 q = B + 16 * lane; q < hi16; q += 512) {
+				uint4 v = *(const uint4 *)(stg + (q & RES_SMASK));
+				*(uint4 *)(win + (q & RES_WMASK)) = v;
+				if (q >= a0) *(uint4 *)(gbase + q) = v;
+				else					// the chunk's first row starts inside a 16-byte row
+					for (u32 k = a0; k < 16; k++) gbase[k] = stg[k];
 			}
-			flushed = upto;
+			if (final) {
+				u32 lo = hi16 > a0 ? hi16 : a0;
+				for (u32 q = lo + lane; q < P; q += 32) gbase[q] = stg[q & RES_SMASK];
+			}
+			B = hi16;
+			__syncwarp();
 		};
 
+		u32 r_next = 0, next_r0 = 0xffffffffu;	// records loaded one group ahead
 		while (r0 < n_rec) {
-			// ---- records of this block, one per thread ------------------------------------
-			const u32 i = r0 + tid;
+			// ---- records of this group, one per lane ----------------------------------------
+			const u32 i = r0 + lane;
 			const bool valid = i < n_rec;
-			u32 r = valid ? rec_end[-1 - (s32)i] : LDB_TOK_PURE_FLAG;
+			u32 r = LDB_TOK_PURE_FLAG;
+			if (next_r0 == r0) r = r_next;
+			else if (valid) r = __ldg(rec_end - 1 - (s32)i);
+			next_r0 = r0 + 32;
+			r_next = (i + 32 < n_rec) ? __ldg(rec_end - 1 - (s32)(i + 32)) : LDB_TOK_PURE_FLAG;
 			u32 lits, mlen = 0, off = 0;
 			if (r & LDB_TOK_PURE_FLAG) {
 				lits = r & 0x7fffffffu;
-				if (tid == 0 && big_rem) lits = big_rem;
+				if (lane == 0 && big_rem) lits = big_rem;
 			} else {
 				lits = (r >> 23) & 255;
 				mlen = ((r >> 15) & 255) + 3;
 				off = (r & 32767) + 1;
 			}
-			if (tid == 0) { misc[1] = 0; misc[2] = lits; }
-			// CTA-wide exclusive prefix sums of {lits, lits + mlen}
+			// warp-wide inclusive prefix sums of {lits, lits + mlen}
 			u32 li = lits, ti = lits + mlen;
+#pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
 				u32 x = __shfl_up_sync(LDB_FULL_MASK, li, o), y = __shfl_up_sync(LDB_FULL_MASK, ti, o);
 				if (lane >= (u32)o) { li += x; ti += y; }
 			}
-			if (lane == 31) { wsum[2 * warp] = li; wsum[2 * warp + 1] = ti; }
-			__syncthreads();
-			u32 lbase = 0, tbase = 0;
-			for (u32 w = 0; w < warp; w++) { lbase += wsum[2 * w]; tbase += wsum[2 * w + 1]; }
-			const u32 lit_src = L + lbase + li - lits;	// first literal of this record
-			const u32 q_lit = P + tbase + ti - lits - mlen;	// where its literals go
+			const u32 lit_src = L + li - lits;		// first literal of this record
+			const u32 q_lit = P + ti - lits - mlen;		// where its literals go
 			const u32 q_m = q_lit + lits;			// where its match goes
 			const u32 q_end = q_m + mlen;
-			// a block never covers more than RES_SPAN bytes: cut it at the first record that would
+			// a group never covers more than RES_SPAN bytes: cut it at the first record that would
 			const bool inc = valid && (q_end - P <= RES_SPAN);
-			const u32 n_inc = (u32)__syncthreads_count(inc);
+			const u32 n_inc = (u32)__popc(__ballot_sync(LDB_FULL_MASK, inc));
 			if (n_inc == 0) {
 				// the first record is a literal run longer than the span: move one span of it
-				const u32 first_lits = misc[2];
-				for (u32 k = tid; k < RES_SPAN; k += RES_THREADS) ring[(P + k) & RES_MASK] = __ldg(lit + L + k);
+				const u32 first_lits = __shfl_sync(LDB_FULL_MASK, lits, 0);
+				for (u32 k = lane; k < RES_SPAN; k += 32) stg[(P + k) & RES_SMASK] = __ldg(lit + L + k);
+				__syncwarp();
 				P += RES_SPAN;
 				L += RES_SPAN;
 				big_rem = first_lits - RES_SPAN;
-				__syncthreads();
-				write_out(P & ~15u);
+				commit(false);
 				continue;
 			}
-			if (inc && tid == n_inc - 1) { misc[3] = q_end; misc[4] = lit_src + lits; }
-
-			// ---- literals, independent matches, pending bits --------------------------------
-			bool pending = false;
-			if (inc) {
-				if (lits <= RES_LIT_FAST) {
-#pragma unroll
-					for (u32 k = 0; k < RES_LIT_FAST; k++)
-						if (k < lits) ring[(q_lit + k) & RES_MASK] = __ldg(lit + lit_src + k);
-				} else {
-					u32 e = atomicAdd((u32 *)&misc[1], 1u);
-					list[3 * e] = q_lit;
-					list[3 * e + 1] = lit_src;
-					list[3 * e + 2] = lits;
-				}
-				if (mlen) {
-					if (q_m - off + mlen <= P) res_copy_match(ring, q_m, off, mlen);
-					else {
-						pending = true;
-						res_bits_set(pend, q_m - P, q_end - P);
-					}
-				}
+			// ---- literal runs and matches out of the window, every lane its own ------------------
+			const bool far = inc && mlen && (q_m - off + mlen <= B);
+			if (inc && lits && lits <= RES_LIT_FAST) res_lit_piece(lit + lit_src, stg, q_lit, lits);
+			if (far) {
+				const u32 s = q_m - off;
+				for (u32 d = 0; d < mlen; d += 16) res_copy_piece(win, stg, q_m + d, s + d, mlen - d < 16 ? mlen - d : 16);
 			}
-			__syncthreads();
-			// long literal runs: one warp per run, 32 bytes per step
-			const u32 n_list = misc[1];
-			if (n_list) {
-				for (u32 e = warp; e < n_list; e += RES_WARPS) {
-					const u32 qd = list[3 * e], src = list[3 * e + 1], n = list[3 * e + 2];
-					for (u32 k = lane; k < n; k += 32) ring[(qd + k) & RES_MASK] = __ldg(lit + src + k);
-				}
+			// long literal runs: the whole warp, 32 bytes per step
+			u32 longs = __ballot_sync(LDB_FULL_MASK, inc && lits > RES_LIT_FAST);
+			while (longs) {
+				const int j = __ffs(longs) - 1;
+				longs &= longs - 1;
+				const u32 qd = __shfl_sync(LDB_FULL_MASK, q_lit, j), src = __shfl_sync(LDB_FULL_MASK, lit_src, j);
+				const u32 n = __shfl_sync(LDB_FULL_MASK, lits, j);
+				for (u32 k = lane; k < n; k += 32) stg[(qd + k) & RES_SMASK] = __ldg(lit + src + k);
 			}
-			// ---- dependent matches, in rounds ----------------------------------------------
-			// needed source bytes: [q_m - off, min(q_m - off + mlen, q_m)); only those at or after P
-			// can be pending
-			u32 need_lo = 0, need_hi = 0;
-			if (pending) {
-				u32 s0 = q_m - off, s1 = s0 + mlen;
-				if (s1 > q_m) s1 = q_m;
-				need_lo = s0 > P ? s0 - P : 0;
-				need_hi = s1 > P ? s1 - P : 0;
+			__syncwarp();
+			// ---- matches that read bytes of this group: in order, the whole warp per match ----------
+			u32 nears = __ballot_sync(LDB_FULL_MASK, inc && mlen && !far);
+			while (nears) {
+				const int j = __ffs(nears) - 1;
+				nears &= nears - 1;
+				const u32 qd = __shfl_sync(LDB_FULL_MASK, q_m, j), o = __shfl_sync(LDB_FULL_MASK, off, j);
+				const u32 n = __shfl_sync(LDB_FULL_MASK, mlen, j);
+				res_copy_coop(win, stg, B, qd, o, n, lane);
+				__syncwarp();
 			}
-			while (__syncthreads_or(pending)) {
-				const bool ready = pending && !(need_hi > need_lo && res_bits_any(pend, need_lo, need_hi));
-				__syncthreads();
-				if (ready) {
-					res_copy_match(ring, q_m, off, mlen);
-					res_bits_clear(pend, q_m - P, q_end - P);
-					pending = false;
-				}
-			}
-			P = misc[3];
-			L = misc[4];
+			// ---- advance, commit the finished rows -----------------------------------------------
+			P = __shfl_sync(LDB_FULL_MASK, q_end, n_inc - 1);
+			L = __shfl_sync(LDB_FULL_MASK, lit_src + lits, n_inc - 1);
 			r0 += n_inc;
 			big_rem = 0;
-			if (r0 >= n_rec) write_out(P);
-			else if (P - flushed >= RES_FLUSH) write_out(P & ~15u);
-			__syncthreads();	// misc[] and the list are rewritten by the next block
+			commit(r0 >= n_rec);
 		}
 	}
 }
@@ -349,10 +312,10 @@ int ldb_launch_inflate_resolve(const ldb_inflate_args &a, const ldb_launch_cfg &
 	LDB_CUDA_CHECK_RET(cudaFuncSetAttribute(ldb_inflate_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SM_BYTES));
 	int per_sm = (cfg.max_smem_optin + 1024) / (RES_SM_BYTES + 1024);
 	if (per_sm < 1) per_sm = 1;
-	if (per_sm > 3) per_sm = 3;
+	if (per_sm > RES_PER_SM) per_sm = RES_PER_SM;
 	size_t blocks = (size_t)cfg.num_sms * per_sm;
 	if (blocks > a.count) blocks = a.count;
-	LDB_LAUNCH(ldb_inflate_resolve_kernel, dim3((unsigned)blocks), dim3(RES_THREADS), RES_SM_BYTES, (cudaStream_t)stream, a, d_counter);
+	LDB_LAUNCH(ldb_inflate_resolve_kernel, dim3((unsigned)blocks), dim3(32), RES_SM_BYTES, (cudaStream_t)stream, a, d_counter);
 	LDB_CUDA_CHECK_RET(cudaGetLastError());
 	return 0;
 }

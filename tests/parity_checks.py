@@ -74,6 +74,21 @@ def check_decompress_valid(ctx, orc, streams):
         assert all(g[0] == 0 and g[1] == s[1] for g, s in zip(got, sel))
 
 
+def check_decompress_large(ctx, sizes=(150000, 262144 + 123), levels=(0, 1, 6, 9)):
+    """Chunks larger than the resolve kernel's 32 KiB window ring (several wraps), stored blocks longer
+    than its staging span (the literal-run path), runs of equal bytes (offset 1, the periodic path)
+    and outputs at every 16-byte phase (the chunks sit back to back in one slab)."""
+    plains = []
+    for k, n in enumerate(sizes):
+        plains += [corpus.text(n, 40 + k), corpus.zeros(n + 1), corpus.pattern(n + 2), corpus.rand(n + 3, k), corpus.mixed(n + 5, k),
+                   (b"ab" * 40 + corpus.text(300, k) + b"x" * 700) * (n // 1800)]
+    for lv in levels:
+        zs = [corpus.zlib_raw(p, lv, zlib.Z_DEFAULT_STRATEGY, -15) for p in plains]
+        got = ctx.decompress_batch_host(zs, [len(p) for p in plains], 0)
+        for p, g in zip(plains, got):
+            assert g[0] == 0 and g[3] == len(p) and g[1] == p, ("large chunk mismatch", lv, len(p), g[0])
+
+
 def fuzz_cases(n_cases, seed, max_size=20000):
     rng = random.Random(seed)
     base = []

@@ -20,6 +20,10 @@ def test_inflate_valid_streams_emulated(emu_ctx, oracle, reflib):
     pc.check_decompress_valid(emu_ctx, oracle, streams)
 
 
+def test_inflate_large_chunks_emulated(emu_ctx):
+    pc.check_decompress_large(emu_ctx, sizes=(150000,), levels=(0, 6))
+
+
 def test_inflate_fuzz_emulated(emu_ctx, oracle):
     v = pc.check_decompress_fuzz(emu_ctx, oracle, pc.fuzz_cases(1500, seed=11))
     assert set(v) >= {0, 1, 3}, v
@@ -73,7 +77,7 @@ def test_gz_front_end_emulated(emu_ctx, emu_api, tmp_path):
 
 
 def test_inflate_output_primitives_unit():
-    """Randomized unit test of the word-accumulator / match-copy primitives (host build)."""
+    """Randomized unit test of the resolve kernel's per-lane copy primitives (host build)."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

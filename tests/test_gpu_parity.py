@@ -66,6 +66,10 @@ def test_decompress_1mib_chunks(gpu_ctx, oracle):
         assert g[0] == 0 and g[1] == p
 
 
+def test_decompress_large_chunks(gpu_ctx):
+    pc.check_decompress_large(gpu_ctx)
+
+
 def test_decompress_fuzz_verdicts(gpu_ctx, oracle):
     seen = pc.check_decompress_fuzz(gpu_ctx, oracle, pc.fuzz_cases(6000, seed=77))
     assert set(seen) == {0, 1, 2, 3}, seen
