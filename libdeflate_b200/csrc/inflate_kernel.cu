@@ -635,34 +635,34 @@ __device__ __forceinline__ void inf_decode_litlen(inf_lane &s, const u8 *sm, con
 		u32 idx = sstart + (bits & ((1u << sb) - 1));
 		e = idx < INF_LSUB_SM ? ltab[tab_idx(INF_LMAIN + idx, lane)] : ovf[idx - INF_LSUB_SM];
 	}
-	u32 cl = e & 15;
+	const u32 cl = e & 15;
 	s.bitpos += cl;
-	if (e < 0x1000) {
-		if (s.n_lit == s.lit_limit) { s.verdict = LDB_INSUFFICIENT_SPACE; s.state = ST_DONE; return; }
-		inf_put_byte(s, e >> 4);
-		return;
+	const bool is_lit = e < 0x1000;
+	// the common case, a literal with room for it, is straight-line predicated code: the 32 lanes
+	// of the warp then share ONE instruction stream for it instead of one per branch target
+	if (is_lit && s.n_lit == s.lit_limit) { s.verdict = LDB_INSUFFICIENT_SPACE; s.state = ST_DONE; return; }
+	const u32 acc2 = __funnelshift_r(s.acc, e >> 4, 8);
+	s.acc = is_lit ? acc2 : s.acc;
+	s.n_lit += is_lit ? 1u : 0u;
+	if (is_lit && (s.n_lit & 3) == 0) *(u32 *)(s.lit + s.n_lit - 4) = s.acc;
+	if (!is_lit) {
+		if (e & LE_EOB_FLAG) {
+			s.verdict = LDB_SUCCESS;
+			s.state = s.is_final ? ST_DONE : ST_HEADER;
+		} else {
+			// length (Appendix A table, ref: deflate_decompress.c:576-587); 'bits' still holds >= 12 bits
+			bits >>= cl;
+			const u32 slot = (e >> 4) & 31;
+			u32 eb = slot >= 8 ? (slot - 4) >> 2 : 0;
+			u32 length = slot >= 8 ? 3 + ((4 + (slot & 3)) << eb) + (bits & ((1u << eb) - 1)) : 3 + slot;
+			if (slot >= 28) { length = 258; eb = 0; }
+			s.bitpos += eb;
+			const bool fits = length <= s.lit_limit - s.n_lit;
+			s.verdict = LDB_INSUFFICIENT_SPACE;	// only read in ST_DONE
+			s.pend_len = length;
+			s.state = fits ? ST_OFF : ST_DONE;
+		}
 	}
-	if (e & LE_EOB_FLAG) {
-		s.verdict = LDB_SUCCESS;
-		s.state = s.is_final ? ST_DONE : ST_HEADER;
-		return;
-	}
-	// length (Appendix A table, ref: deflate_decompress.c:576-587); 'bits' still holds >= 12 bits
-	bits >>= cl;
-	u32 slot = (e >> 4) & 31;
-	u32 length;
-	if (slot < 8) {
-		length = 3 + slot;
-	} else if (slot < 28) {
-		u32 eb = (slot - 4) >> 2;
-		length = 3 + ((4 + (slot & 3)) << eb) + (bits & ((1u << eb) - 1));
-		s.bitpos += eb;
-	} else {
-		length = 258;
-	}
-	if (length > s.lit_limit - s.n_lit) { s.verdict = LDB_INSUFFICIENT_SPACE; s.state = ST_DONE; return; }
-	s.pend_len = length;
-	s.state = ST_OFF;
 }
 
 // inf_decode_offset: the offset of the pending length; emits the match record.

@@ -6,21 +6,23 @@
 // forward byte-by-byte overlap semantics) -- from the chunk's token stream: packed literal
 // bytes + 4-byte {literal run, length, offset} records (format: ldb_common.cuh).
 //
-// B200 mapping -- ONE WARP per chunk, six single-warp CTAs per SM, no block barriers:
+// B200 mapping -- ONE WARP per chunk, 16 single-warp CTAs per SM, no block barriers:
 //   * LZ77 text has dependency chains hundreds of matches deep (every occurrence of a frequent
 //     word copies from the previous one), so the chunk is walked in order, 32 records (one per
 //     lane) at a time, and what counts is the latency of one dependent step and how many chunks
-//     an SM holds.  Shared memory per chunk: the 32 KiB window as a ring (committed bytes only)
-//     + a 4 KiB staging ring in which the current group is assembled = 36 KiB, 6 chunks per SM;
-//     the window never touches L2/HBM;
+//     an SM holds.  Shared memory per chunk: a 4 KiB staging ring in which the current group is
+//     assembled.  The 32 KiB window is the chunk's own committed output, read back through
+//     L1/L2: 148 x 16 windows = 74 MB stay resident in the 126 MB L2 (measured first with the
+//     window as a shared-memory ring: 36 KiB per chunk, 6 warps per SM, 0.14 IPC per warp --
+//     profiles/r02_inflate_b.md);
 //   * per group: two warp prefix sums ({literals}, {literals + length}) give every lane its
 //     literal source and its destination; all literal runs and all matches whose source lies in
 //     the window ("far": ~90 % of them) are copied by their own lanes at once, 16 bytes per step
 //     (aligned word loads, funnel shifts, word stores); the few matches that read bytes of the
 //     group itself are then done one after the other by the WHOLE warp, a byte per lane (the
 //     byte-by-byte overlap rule becomes index arithmetic: byte k comes from k mod offset);
-//   * finished 16-byte rows go staging -> window ring and staging -> global in the same pass:
-//     coalesced 16-byte stores are the only global stores of the kernel.
+//   * finished 16-byte rows go staging -> global: coalesced 16-byte stores are the only global
+//     stores of the kernel.
 // (A block-parallel version with exact dependency tracking in rounds was measured first: 232 K
 // warp instructions per chunk, ~50 rounds per 256 records on Zipf text -- profiles/r02_inflate_a.md.)
 //
@@ -28,15 +30,13 @@
 // is the price of the two-kernel split; see inflate_kernel.cu).
 #include "ldb_common.cuh"
 
-#define RES_WIN     32768u	// window ring: committed bytes, position q lives at q % 32768
-#define RES_WMASK   (RES_WIN - 1)
 #define RES_STG     4096u	// staging ring: the group being assembled, position q at q % 4096
 #define RES_SMASK   (RES_STG - 1)
 #define RES_SPAN    2048u	// most output bytes one group of records may cover
 #define RES_LIT_FAST 16u	// literal runs up to this are placed by the owning lane in one step
-#define RES_SM_BYTES (RES_WIN + RES_STG)
+#define RES_SM_BYTES RES_STG
 #ifndef RES_PER_SM
-#define RES_PER_SM  6
+#define RES_PER_SM  16		// warps (= chunks) per SM: 148 x 16 windows of 32 KiB = 74 MB stay L2-resident
 #endif
 
 // the scratch slot of a chunk: what the decoder can emit is bounded both by the output room
@@ -119,17 +119,19 @@ __device__ __forceinline__ void res_store16(u8 *stg, u32 qd, u32 m, u32 v0, u32 
 	}
 }
 
-// m <= 16 bytes from window position qs (committed bytes) to staging position qd
+// m <= 16 bytes from window position qs (committed bytes: the chunk's own output, read back
+// through L1/L2) to staging position qd.  Only words that hold a wanted byte are loaded, so no
+// load goes past the committed rows.
 __device__ __forceinline__ void res_copy_piece(const u8 *win, u8 *stg, u32 qd, u32 qs, u32 m)
 {
-	const u32 *r32 = (const u32 *)win;
-	const u32 sa = qs & ~3u, ssh = 8 * (qs & 3);
+	const u32 *r32 = (const u32 *)(win + (qs & ~3u));
+	const u32 ssh = 8 * (qs & 3);
 	const u32 need = (qs & 3) + m;		// source bytes counted from the aligned start
-	u32 w0 = r32[(sa & RES_WMASK) >> 2], w1 = 0, w2 = 0, w3 = 0, w4 = 0;
-	if (need > 4) w1 = r32[((sa + 4) & RES_WMASK) >> 2];
-	if (need > 8) w2 = r32[((sa + 8) & RES_WMASK) >> 2];
-	if (need > 12) w3 = r32[((sa + 12) & RES_WMASK) >> 2];
-	if (need > 16) w4 = r32[((sa + 16) & RES_WMASK) >> 2];
+	u32 w0 = r32[0], w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+	if (need > 4) w1 = r32[1];
+	if (need > 8) w2 = r32[2];
+	if (need > 12) w3 = r32[3];
+	if (need > 16) w4 = r32[4];
 	res_store16(stg, qd, m, __funnelshift_r(w0, w1, ssh), __funnelshift_r(w1, w2, ssh),
 		    __funnelshift_r(w2, w3, ssh), __funnelshift_r(w3, w4, ssh));
 }
@@ -160,7 +162,7 @@ __device__ __forceinline__ void res_copy_coop(const u8 *win, u8 *stg, u32 B, u32
 		for (u32 k = lane; k - lane < n; k += 32) {
 			if (k < n) {
 				u32 s = s0 + k;
-				u8 b = s < B ? win[s & RES_WMASK] : stg[s & RES_SMASK];
+				u8 b = s < B ? win[s] : stg[s & RES_SMASK];
 				stg[(qd + k) & RES_SMASK] = b;
 			}
 			__syncwarp();
@@ -169,7 +171,7 @@ __device__ __forceinline__ void res_copy_coop(const u8 *win, u8 *stg, u32 B, u32
 		// periodic: byte k repeats byte k mod offset of the offset bytes before the destination
 		for (u32 k = lane; k < n; k += 32) {
 			u32 s = s0 + k % off;
-			u8 b = s < B ? win[s & RES_WMASK] : stg[s & RES_SMASK];
+			u8 b = s < B ? win[s] : stg[s & RES_SMASK];
 			stg[(qd + k) & RES_SMASK] = b;
 		}
 	}
@@ -180,8 +182,7 @@ __global__ void __launch_bounds__(32)
 ldb_inflate_resolve_kernel(ldb_inflate_args a, u32 *work_counter)
 {
 	LDB_DYN_SMEM(sm);
-	u8 *win = sm;
-	u8 *stg = sm + RES_WIN;
+	u8 *stg = sm;
 	const u32 lane = threadIdx.x;
 
 	for (;;) {
@@ -199,6 +200,7 @@ ldb_inflate_resolve_kernel(ldb_inflate_args a, u32 *work_counter)
 		// destination: 16-byte rows of the two rings are 16-byte rows of global memory
 		const u32 a0 = (u32)(uintptr_t)out & 15;
 		u8 *const gbase = out - a0;
+		const u8 *const win = gbase;	// the window: committed rows of the chunk's own output
 		u32 P = a0;		// where the next group starts writing
 		u32 B = 0;		// rows below B (a multiple of 16) are committed: in the window and in 'out'
 		u32 L = 0;		// literal bytes consumed
@@ -211,7 +213,6 @@ ldb_inflate_resolve_kernel(ldb_inflate_args a, u32 *work_counter)
 			const u32 hi16 = P & ~15u;
 			for (u32 q = B + 16 * lane; q < hi16; q += 512) {
 				uint4 v = *(const uint4 *)(stg + (q & RES_SMASK));
-				*(uint4 *)(win + (q & RES_WMASK)) = v;
 				if (q >= a0) *(uint4 *)(gbase + q) = v;
 				else					// the chunk's first row starts inside a 16-byte row
 					for (u32 k = a0; k < 16; k++) gbase[k] = stg[k];

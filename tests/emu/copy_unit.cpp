@@ -10,11 +10,11 @@ int ldb_fail(int err, const char *, const char *, int) { return err; }
 int main() {
     std::mt19937 rng(1);
     int bad = 0;
-    std::vector<u8> winv(RES_WIN + 64), stgv(RES_STG + 64), litv(4096 + 64);
+    std::vector<u8> winv((1u << 20) + 64), stgv(RES_STG + 64), litv(4096 + 64);
     u8 *win = (u8 *)(((uintptr_t)winv.data() + 15) & ~(uintptr_t)15);
     u8 *stg = (u8 *)(((uintptr_t)stgv.data() + 15) & ~(uintptr_t)15);
     u8 *lit = (u8 *)(((uintptr_t)litv.data() + 15) & ~(uintptr_t)15);
-    for (u32 i = 0; i < RES_WIN; i++) win[i] = (u8)rng();
+    for (u32 i = 0; i < (1u << 20) + 32; i++) win[i] = (u8)rng();
     for (u32 i = 0; i < 4096; i++) lit[i] = (u8)rng();
     for (int iter = 0; iter < 200000 && bad < 5; iter++) {
         for (u32 i = 0; i < RES_STG; i++) stg[i] = (u8)(i * 7 + iter);
@@ -24,7 +24,7 @@ int main() {
         u32 qs = rng() % (1u << 20), ls = 4 + rng() % 4000;
         if (from_lit) res_lit_piece(lit + ls, stg, qd, m);
         else res_copy_piece(win, stg, qd, qs, m);
-        for (u32 k = 0; k < m; k++) before[(qd + k) & RES_SMASK] = from_lit ? lit[ls + k] : win[(qs + k) & RES_WMASK];
+        for (u32 k = 0; k < m; k++) before[(qd + k) & RES_SMASK] = from_lit ? lit[ls + k] : win[qs + k];
         if (memcmp(before.data(), stg, RES_STG)) { bad++; printf("iter %d mismatch qd %u qs %u m %u lit %d\n", iter, qd, qs, m, (int)from_lit); }
     }
     printf("bad %d\n", bad);
