@@ -84,13 +84,7 @@
 #define INF_OVF_ENTRIES (INF_OVF_L + INF_OVF_O)
 
 #ifndef INF_QUANTUM
-#define INF_QUANTUM   96		// decode iterations between service phases
-#endif
-#ifndef INF_LIT_ROUNDS
-#define INF_LIT_ROUNDS 4		// litlen rounds per match round
-#endif
-#ifndef INF_LIT_MIN_LANES
-#define INF_LIT_MIN_LANES 10	// stop the litlen rounds when fewer lanes than this still decode literals
+#define INF_QUANTUM   384		// decode steps between service phases
 #endif
 
 // per-warp shared memory layout (bytes)
@@ -110,10 +104,13 @@ static_assert(INF_O_ENTRIES >= 64, "the offset region doubles as the 128-byte pr
 static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry");
 
 // entry encodings (u16)
+// bits 15..14: 0 literal (value << 4 | codeword bits), 1 "value" symbol = length or offset slot
+// (slot << 4 | bits), 2 end of block, 3 subtable pointer ((start / 2) << 4 | index bits).  Litlen and
+// offset tables share the encoding, so one instruction stream decodes either.
 #define LE_LEN_FLAG  0x4000u
 #define LE_EOB_FLAG  0x8000u
 #define LE_SUB_FLAG  0xC000u
-#define OE_SUB_FLAG  0x8000u
+#define OE_SUB_FLAG  LE_SUB_FLAG
 
 // ST_LIT: the next thing in the stream is a litlen symbol; ST_OFF: a length has been decoded, its
 // offset is next; ST_DONE: the stream has ended with s.verdict (finished in the service phase)
@@ -473,7 +470,7 @@ __device__ bool inf_build_table(const u32 (&mylen)[NROWS], u8 *sm, u32 tab_off, 
 			return LE_LEN_FLAG | (slot << 4) | len;
 		} else {
 			u32 slot = sym > 29 ? 29 : sym;	// syms 30/31 decode as base 24577 (deflate_decompress.c:627)
-			return (slot << 4) | len;
+			return LE_LEN_FLAG | (slot << 4) | len;
 		}
 	};
 
@@ -610,90 +607,83 @@ __device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
 	return sym < 144 ? 8 : (sym < 256 ? 9 : (sym < 280 ? 7 : 8));
 }
 
-// ---- decoding, split in two so that the warp can run several cheap litlen rounds (most
-// symbols are literals) before it pays for ONE offset round with many lanes in it -----------
-// Both functions end the stream by moving to ST_DONE with a verdict; the bookkeeping of a finished
-// stream happens once per service phase, outside the hot loop.
-//
-// inf_decode_litlen: one litlen symbol.  Literal -> emitted.  End of block -> ST_HEADER, or ST_DONE
-// when the block was the final one.  Length -> ST_OFF with s.pend_len set.
-__device__ __forceinline__ void inf_decode_litlen(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
+// ---- decoding: ONE step function for both alphabets -------------------------------------------
+// A lane is either about to read a litlen symbol (ST_LIT) or the offset symbol of a pending length
+// (ST_OFF).  Both are "look up table[bits & mask], maybe a subtable, consume the codeword"; a length
+// and an offset are both "base(slot) + extra bits" with the same arithmetic up to a constant
+// k (2 for lengths, 1 for offsets: Appendix A tables, ref: deflate_decompress.c:576-587, 616-627).
+// So the 32 lanes of a warp execute one instruction stream per step whatever their symbols are, and
+// no lane ever waits for another lane's alphabet.  The kernel is bound by the integer pipe, so
+// what counts is the number of instructions per step.
+// The stream ends by moving to ST_DONE with a verdict; the bookkeeping of a finished stream
+// happens once per service phase, outside this loop.
+__device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
 {
-	const u16 *ltab = (const u16 *)(sm + INF_SM_LTAB);
+	// (written without early returns: one merge point keeps the loop-carried registers in place)
+	const bool isoff = s.state == ST_OFF;
 	u32 bits = inf_peek(s);
-	if (s.wpos + 8 > s.in_nal) {
-		// virtual zero bytes are (nearly) in play: P >= 8n+9 means the reference's refill
-		// over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
-		if (inf_bits_past_end(s) >= 9) { s.verdict = LDB_BAD_DATA; s.state = ST_DONE; return; }
+	bool dead = false;
+	if (!isoff && s.wpos + 8 > s.in_nal) {
+		// start of a litlen symbol with virtual zero bytes (nearly) in play: P >= 8n+9 means the
+		// reference's refill over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
+		dead = inf_bits_past_end(s) >= 9;
 	}
-	u32 e = ltab[tab_idx(bits & (INF_LMAIN - 1), lane)];
-	if (e >= LE_SUB_FLAG) {
-		u32 sstart = ((e >> 4) & 0x3ff) << 1;
-		u32 sb = e & 15;
-		bits >>= INF_LB;
-		s.bitpos += INF_LB;
-		u32 idx = sstart + (bits & ((1u << sb) - 1));
-		e = idx < INF_LSUB_SM ? ltab[tab_idx(INF_LMAIN + idx, lane)] : ovf[idx - INF_LSUB_SM];
-	}
-	const u32 cl = e & 15;
-	s.bitpos += cl;
-	const bool is_lit = e < 0x1000;
-	// the common case, a literal with room for it, is straight-line predicated code: the 32 lanes
-	// of the warp then share ONE instruction stream for it instead of one per branch target
-	if (is_lit && s.n_lit == s.lit_limit) { s.verdict = LDB_INSUFFICIENT_SPACE; s.state = ST_DONE; return; }
-	const u32 acc2 = __funnelshift_r(s.acc, e >> 4, 8);
-	s.acc = is_lit ? acc2 : s.acc;
-	s.n_lit += is_lit ? 1u : 0u;
-	if (is_lit && (s.n_lit & 3) == 0) *(u32 *)(s.lit + s.n_lit - 4) = s.acc;
-	if (!is_lit) {
-		if (e & LE_EOB_FLAG) {
+	if (dead) {
+		s.verdict = LDB_BAD_DATA;
+		s.state = ST_DONE;
+	} else {
+		const u16 *tab = (const u16 *)(sm + (isoff ? INF_SM_OTAB : INF_SM_LTAB)) + lane;
+		const u32 mainbits = isoff ? INF_OB : INF_LB;
+		u32 e = tab[(bits & ((1u << mainbits) - 1)) * 32];
+		if (e >= LE_SUB_FLAG) {
+			const u32 sstart = ((e >> 4) & 0x3ff) << 1;
+			const u32 sb = e & 15;
+			bits >>= mainbits;
+			s.bitpos += mainbits;
+			const u32 idx = sstart + (bits & ((1u << sb) - 1));
+			const u32 sub_sm = isoff ? INF_OSUB_SM : INF_LSUB_SM;
+			e = idx < sub_sm ? tab[((1u << mainbits) + idx) * 32] : ovf[(isoff ? INF_OVF_L : 0) + idx - sub_sm];
+		}
+		const u32 cl = e & 15;
+		s.bitpos += cl;
+		if (e < LE_LEN_FLAG) {
+			// literal (only litlen tables hold them)
+			if (s.n_lit == s.lit_limit) {
+				s.verdict = LDB_INSUFFICIENT_SPACE;
+				s.state = ST_DONE;
+			} else {
+				inf_put_byte(s, e >> 4);
+			}
+		} else if (e & LE_EOB_FLAG) {
 			s.verdict = LDB_SUCCESS;
 			s.state = s.is_final ? ST_DONE : ST_HEADER;
 		} else {
-			// length (Appendix A table, ref: deflate_decompress.c:576-587); 'bits' still holds >= 12 bits
+			// length or offset: base(slot) + extra bits
 			bits >>= cl;
 			const u32 slot = (e >> 4) & 31;
-			u32 eb = slot >= 8 ? (slot - 4) >> 2 : 0;
-			u32 length = slot >= 8 ? 3 + ((4 + (slot & 3)) << eb) + (bits & ((1u << eb) - 1)) : 3 + slot;
-			if (slot >= 28) { length = 258; eb = 0; }
+			const u32 k = isoff ? 1 : 2;			// slots per doubling = 1 << k
+			const u32 first = 2u << k;			// first slot with extra bits: 4 (offsets), 8 (lengths)
+			const u32 origin = isoff ? 1 : 3;
+			u32 eb = slot >= first ? (slot - (1u << k)) >> k : 0;
+			u32 val = slot >= first ? origin + (((1u << k) + (slot & ((1u << k) - 1))) << eb) : origin + slot;
+			if (!isoff && slot >= 28) { val = 258; eb = 0; }	// the one irregular entry: length 258, no extra bits
+			val += bits & ((1u << eb) - 1);
 			s.bitpos += eb;
-			const bool fits = length <= s.lit_limit - s.n_lit;
-			s.verdict = LDB_INSUFFICIENT_SPACE;	// only read in ST_DONE
-			s.pend_len = length;
-			s.state = fits ? ST_OFF : ST_DONE;
+			if (!isoff) {
+				// length: "no room" is decided before the offset is looked at (decompress_template.h:696-701)
+				const bool fits = val <= s.lit_limit - s.n_lit;
+				s.verdict = LDB_INSUFFICIENT_SPACE;	// only read in ST_DONE
+				s.pend_len = val;
+				s.state = fits ? ST_OFF : ST_DONE;
+			} else if (val > inf_out_pos(s)) {
+				s.verdict = LDB_BAD_DATA;
+				s.state = ST_DONE;
+			} else {
+				inf_put_match(s, s.pend_len, val);
+				s.state = ST_LIT;
+			}
 		}
 	}
-}
-
-// inf_decode_offset: the offset of the pending length; emits the match record.
-__device__ __forceinline__ void inf_decode_offset(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
-{
-	const u16 *otab = (const u16 *)(sm + INF_SM_OTAB);
-	u32 bits = inf_peek(s);
-	u32 oe = otab[tab_idx(bits & (INF_OMAIN - 1), lane)];
-	if (oe & OE_SUB_FLAG) {
-		u32 sstart = ((oe >> 4) & 0x3ff) << 1;
-		u32 sb = oe & 15;
-		bits >>= INF_OB;
-		s.bitpos += INF_OB;
-		u32 idx = sstart + (bits & ((1u << sb) - 1));
-		oe = idx < INF_OSUB_SM ? otab[tab_idx(INF_OMAIN + idx, lane)] : ovf[INF_OVF_L + idx - INF_OSUB_SM];
-	}
-	u32 ocl = oe & 15;
-	bits >>= ocl;
-	s.bitpos += ocl;
-	u32 oslot = (oe >> 4) & 31;
-	u32 offset;
-	if (oslot < 4) {
-		offset = 1 + oslot;
-	} else {
-		u32 eb = (oslot - 2) >> 1;
-		offset = 1 + ((2 + (oslot & 1)) << eb) + (bits & ((1u << eb) - 1));
-		s.bitpos += eb;
-	}
-	if (offset > inf_out_pos(s)) { s.verdict = LDB_BAD_DATA; s.state = ST_DONE; return; }
-	inf_put_match(s, s.pend_len, offset);
-	s.state = ST_LIT;
 }
 
 // ---- the decode kernel --------------------------------------------------------------
@@ -878,21 +868,11 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 		}
 		if (__all_sync(LDB_FULL_MASK, s.state == ST_IDLE && exhausted)) break;
 
-		// ---- decode phase ----------------------------------------------------
+		// ---- decode phase: INF_QUANTUM steps, one symbol per lane and step ---------------------
 #pragma unroll 1
 		for (int it = 0; it < INF_QUANTUM; it++) {
-			// litlen rounds: lanes keep decoding literals until they hit a length (or the end
-			// of their block); stops early once most lanes wait for the offset round
-#pragma unroll 1
-			for (int r = 0; r < INF_LIT_ROUNDS; r++) {
-				if (s.state == ST_LIT) inf_decode_litlen(s, sm, ovf, lane);
-				if (r + 1 < INF_LIT_ROUNDS &&
-				    __popc(__ballot_sync(LDB_FULL_MASK, s.state == ST_LIT)) < INF_LIT_MIN_LANES)
-					break;
-			}
-			// offset round: the offsets of the pending lengths, one record each
-			if (s.state == ST_OFF) inf_decode_offset(s, sm, ovf, lane);
-			if ((it & 15) == 15 && !__any_sync(LDB_FULL_MASK, s.state >= ST_LIT)) break;
+			if (s.state >= ST_LIT) inf_decode_step(s, sm, ovf, lane);
+			if ((it & 31) == 31 && !__any_sync(LDB_FULL_MASK, s.state >= ST_LIT)) break;
 		}
 		__syncwarp();
 	}

@@ -6,13 +6,14 @@
 // forward byte-by-byte overlap semantics) -- from the chunk's token stream: packed literal
 // bytes + 4-byte {literal run, length, offset} records (format: ldb_common.cuh).
 //
-// B200 mapping -- ONE WARP per chunk, 16 single-warp CTAs per SM, no block barriers:
+// B200 mapping -- ONE WARP per chunk, 32 single-warp CTAs per SM, no block barriers:
 //   * LZ77 text has dependency chains hundreds of matches deep (every occurrence of a frequent
 //     word copies from the previous one), so the chunk is walked in order, 32 records (one per
 //     lane) at a time, and what counts is the latency of one dependent step and how many chunks
 //     an SM holds.  Shared memory per chunk: a 4 KiB staging ring in which the current group is
 //     assembled.  The 32 KiB window is the chunk's own committed output, read back through
-//     L1/L2: 148 x 16 windows = 74 MB stay resident in the 126 MB L2 (measured first with the
+//     L1/L2 (148 x 32 windows of 32 KiB; the recently written part of each is what matches mostly
+//     reach for, and the 126 MB L2 holds it) (measured first with the
 //     window as a shared-memory ring: 36 KiB per chunk, 6 warps per SM, 0.14 IPC per warp --
 //     profiles/r02_inflate_b.md);
 //   * per group: two warp prefix sums ({literals}, {literals + length}) give every lane its
@@ -36,7 +37,7 @@
 #define RES_LIT_FAST 16u	// literal runs up to this are placed by the owning lane in one step
 #define RES_SM_BYTES RES_STG
 #ifndef RES_PER_SM
-#define RES_PER_SM  16		// warps (= chunks) per SM: 148 x 16 windows of 32 KiB = 74 MB stay L2-resident
+#define RES_PER_SM  32		// warps (= chunks) per SM; measured 8 / 16 / 24 / 32: 25.9 / 14.2 / 10.6 / 9.0 ms per 4 GiB
 #endif
 
 // the scratch slot of a chunk: what the decoder can emit is bounded both by the output room

@@ -13,14 +13,11 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    # resolve kernel: warps (= chunks whose 32 KiB window must stay in L2) per SM
-    "r8": ["-DRES_PER_SM=8"],
-    "r24": ["-DRES_PER_SM=24"],
-    "r32": ["-DRES_PER_SM=32"],
-    # decode kernel: literal rounds per offset round
-    "l3": ["-DINF_LIT_ROUNDS=3"],
-    "l6": ["-DINF_LIT_ROUNDS=6"],
+    # decode kernel: steps between service phases
+    "q128": ["-DINF_QUANTUM=128"],
+    "q1024": ["-DINF_QUANTUM=1024"],
 }
+# resolve kernel, warps (= chunks) per SM, -DRES_PER_SM=8/16/24/32: 25.9 / 14.2 / 10.6 / 9.0 ms per 65536 x 64 KiB
 # measured and dropped: resumable chain walk of the deflate search (-DLZ_QUANTUM=6/8/12): 86.9 / 86.4 / 84.3 ms vs 79.2 ms
 # per 16384 chunks (profiles/r02_deflate_quantum_ab.md)
 
