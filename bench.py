@@ -175,7 +175,8 @@ def cpu_roundtrip(cpub, fmt, level, host_in, chunk, n, threads, want_streams=Fal
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation on the host cores."""
+    """--impl reference: the reference's own CPU implementation on the host cores, on the SAME
+    batch shape as the GPU arm (identical `config`), bounded only if the host is too slow for it."""
     rank, world, local = dist_env()
     if rank != 0:
         return
@@ -186,34 +187,48 @@ def run_reference(args):
     synth = load_synth()
     threads = host_threads()
     chunk = args.chunk_size
-    # bounded sample of the same workload: ~512 chunks per host thread per step
-    n = max(1024, min(args.chunks, 512 * threads))
+    n = args.chunks
     buf = (ctypes.c_uint8 * (n * chunk))()
     synth.synth_fill(buf, chunk, 0, n, 0, threads)
     fmt = 2 if args.workload == "roundtrip" else 0
     times = []
     ratio = None
+    bounded = None
     for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         tc, td, total, streams = cpu_roundtrip(cpub, fmt, LEVEL, buf, chunk, n, threads, want_streams=(args.workload == "decompress"))
         ratio = total / float(n * chunk)
         t = (tc + td) if args.workload == "roundtrip" else td
         if it >= args.warmup:
-            times.append((t, tc, td))
+            times.append((t, tc, td, n))
+        if it == 0:
+            # a host with very few usable CPUs: keep the whole run within a few minutes by sampling the batch
+            per_pass = time.perf_counter() - t0
+            budget = 180.0 / (args.warmup + args.steps)
+            while per_pass > budget and n > 1024:
+                n //= 2
+                per_pass /= 2
+                bounded = n
     tsum = sum(t[0] for t in times)
-    value = n * chunk * len(times) / 1e6 / tsum
+    nbytes = sum(t[3] for t in times) * chunk
+    value = nbytes / 1e6 / tsum
+    cfg = workload_config(args)
+    if bounded:
+        cfg["reference_sample"] = "first %d chunks per step (host too slow for the full batch within the time budget)" % bounded
     line = {
         "impl": "reference",
         "metric": metric_name(args), "value": round(value, 2), "unit": "MB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * tsum / len(times), 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, n_override=n),
+        "config": cfg,
         "cpu_baseline": {"value": round(value, 2), "unit": "MB/s", "cores": threads, "host_cpus_online": os.cpu_count(), "cpu_quota": cpu_quota(), "kind": "reference",
+                         "per_thread_MBps": round(value / threads, 2),
                          "sample": "%d x %d B chunks per step, gzip L%d compress+decompress with oracle/_ref (unmodified libdeflate), %d threads"
                                    % (n, chunk, LEVEL, threads) if args.workload == "roundtrip" else
                                    "%d x %d B chunks per step, raw DEFLATE decompress of reference L%d streams, %d threads" % (n, chunk, LEVEL, threads),
-                         "compress_MBps": round(n * chunk * len(times) / 1e6 / sum(t[1] for t in times), 2),
-                         "decompress_MBps": round(n * chunk * len(times) / 1e6 / sum(t[2] for t in times), 2),
+                         "compress_MBps": round(nbytes / 1e6 / sum(t[1] for t in times), 2),
+                         "decompress_MBps": round(nbytes / 1e6 / sum(t[2] for t in times), 2),
                          "ratio": round(ratio, 4)},
         "e2e": {"value": round(value, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -240,13 +255,15 @@ def workload_config(args, n_override=None):
 
 
 class DeviceBatch:
-    """Device-resident batch: a slab plus device arrays of pointers/sizes."""
+    """Device-resident batch: a slab (owned, or a view of another batch's slab) plus device arrays
+    of pointers/sizes."""
 
-    def __init__(self, ctx, n, stride):
+    def __init__(self, ctx, n, stride, slab=None):
         import numpy as np
         self.ctx, self.n, self.stride = ctx, n, stride
         l = ctx.l
-        self.slab = l.libdeflate_b200_device_malloc(ctx.h, n * stride + 256)
+        self.own = slab is None
+        self.slab = l.libdeflate_b200_device_malloc(ctx.h, n * stride + 256) if slab is None else slab
         self.d_ptrs = l.libdeflate_b200_device_malloc(ctx.h, 8 * n)
         self.d_sizes = l.libdeflate_b200_device_malloc(ctx.h, 8 * n)
         assert self.slab and self.d_ptrs and self.d_sizes, "device_malloc failed"
@@ -261,8 +278,68 @@ class DeviceBatch:
         self.ctx.sync()
 
     def free(self):
-        for p in (self.slab, self.d_ptrs, self.d_sizes):
+        for p in ((self.slab,) if self.own else ()) + (self.d_ptrs, self.d_sizes):
             self.ctx.l.libdeflate_b200_device_free(self.ctx.h, p)
+
+
+def timed_steps(ctx, l, step, steps, warmup, barrier=None, clocks=None):
+    """W untimed steps, then K steps between two CUDA events on the launching stream; per-kernel
+    device time from the library's own event pairs around every launch in the same region."""
+    for _ in range(warmup):
+        step()
+    ctx.sync()
+    l.libdeflate_b200_ctx_set_profiling(ctx.h, 1)
+    l.libdeflate_b200_kernel_time_reset(ctx.h)
+    launches0 = ctx.launches
+    if barrier:
+        barrier()
+    ctx.sync()
+    if clocks:
+        clocks.start()
+    l.libdeflate_b200_timer_start(ctx.h)
+    for _ in range(steps):
+        step()
+    ms = max(l.libdeflate_b200_timer_stop_ms(ctx.h), 1e-9)
+    ctx.sync()
+    if barrier:
+        barrier()
+    clk = clocks.stop() if clocks else None
+    launches = ctx.launches - launches0
+    ktime = {}
+    for name, k in KIND.items():
+        cnt = ctypes.c_uint64(0)
+        t = l.libdeflate_b200_kernel_time_ms(ctx.h, k, ctypes.byref(cnt))
+        ktime[name] = (t, cnt.value)
+    l.libdeflate_b200_ctx_set_profiling(ctx.h, 0)
+    return ms, ktime, launches, clk
+
+
+def load_traffic(key):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(key, {})
+    except Exception:
+        return {}
+
+
+def roofline_entry(kernels, ms_total, launches, alg_bytes, traffic_db, traffic_key, peak, peak_src):
+    """achieved = algorithmic bytes per launch / average duration of the named kernel(s)."""
+    if not launches or ms_total <= 0:
+        return None
+    per = ms_total / launches / 1e3
+    ach = alg_bytes / per / 1e9
+    tr = 0.0
+    for k in kernels:
+        v = traffic_db.get(k, {}).get("dram_bytes_per_launch")
+        if not v:
+            tr = None
+            break
+        tr += v
+    return {"kernel": " + ".join(kernels), "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+            "frac": round(ach / peak, 4), "traffic": int(tr) if tr else None,
+            "traffic_over_algorithmic": round(tr / alg_bytes, 3) if tr else None,
+            "traffic_source": ("profiles/dram_traffic.json[%s] (ncu dram__bytes_read+write of this build, same configuration)" % traffic_key) if tr else None,
+            "peak_source": peak_src,
+            "avg_launch_ms": round(per * 1e3, 4), "algorithmic_bytes_per_launch": int(alg_bytes)}
 
 
 def run_b200(args):
@@ -301,8 +378,9 @@ def run_b200(args):
     threads = max(1, host_threads() // max(1, world))
     n, chunk = args.chunks, args.chunk_size
     fmt = ldb.GZIP if args.workload == "roundtrip" else ldb.RAW
-    bound = getattr(l, "libdeflate_%s_compress_bound" % ("gzip" if fmt == ldb.GZIP else "deflate"))(None, chunk)
+    bound = l.libdeflate_gzip_compress_bound(None, chunk)
     cstride = (bound + 15) & ~15
+    peak, peak_src = load_peaks()
 
     # ---- inputs: synthetic chunks generated on the host (pinned), then resident in HBM ----
     pin_in = l.libdeflate_b200_pinned_malloc(n * chunk)
@@ -320,77 +398,69 @@ def run_b200(args):
     d_aout = l.libdeflate_b200_device_malloc(ctx.h, 8 * n)
     d_res = l.libdeflate_b200_device_malloc(ctx.h, 4 * n)
 
-    ref_ratio = None
-    if args.workload == "decompress":
-        # the reference's own L6 raw streams for the same chunks
-        assert cpub is not None, "decompress workload needs oracle/_ref (prebuilt from /root/reference)"
+    def load_reference_streams():
+        """the reference's own L6 raw streams for the same chunks -> d_comp / d_csz"""
+        assert cpub is not None, "the decompress workload needs oracle/_ref (prebuilt from /root/reference)"
         comp = (ctypes.c_uint8 * (cstride * n))()
         sizes = (ctypes.c_size_t * n)()
         fails = ctypes.c_int(0)
-        cpub.cpub_compress(0, LEVEL, pin_in, chunk, n, comp, cstride, sizes, host_threads() // max(1, world), ctypes.byref(fails))
+        cpub.cpub_compress(0, 6, pin_in, chunk, n, comp, cstride, sizes, threads, ctypes.byref(fails))
         assert fails.value == 0
         ctx._check(l.libdeflate_b200_memcpy_h2d(ctx.h, d_comp.slab, comp, cstride * n), "h2d")
-        csz = np.frombuffer(sizes, dtype=np.uint64).copy()
-        ctx._check(l.libdeflate_b200_memcpy_h2d(ctx.h, d_csz, csz.ctypes.data, 8 * n), "h2d")
+        cs = np.frombuffer(sizes, dtype=np.uint64).copy()
+        ctx._check(l.libdeflate_b200_memcpy_h2d(ctx.h, d_csz, cs.ctypes.data, 8 * n), "h2d")
         ctx.sync()
-        ref_ratio = float(csz.sum()) / (n * chunk)
-        del comp
+        return cs
+
+    def decompress_step(f):
+        ctx._check(l.libdeflate_b200_decompress_batch(ctx.h, f, 0, d_comp.d_ptrs, d_csz, d_out.d_ptrs, d_out.d_sizes, None, d_aout, d_res, n), "decompress_batch")
+
+    def check_outputs(what, verdicts=True):
+        if verdicts:
+            res = np.empty(n, dtype=np.int32)
+            aout = np.empty(n, dtype=np.uint64)
+            ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, res.ctypes.data, d_res, 4 * n), "d2h")
+            ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, aout.ctypes.data, d_aout, 8 * n), "d2h")
+            ctx.sync()
+            assert (res == 0).all(), "%s: decompress verdicts not all SUCCESS: %s" % (what, np.unique(res, return_counts=True))
+            assert (aout == chunk).all(), "%s: decompressed sizes wrong" % what
+        # checksum of checksums over every chunk (device CRC-32 of outputs vs inputs)
+        d_c1 = l.libdeflate_b200_device_malloc(ctx.h, 4 * n)
+        d_c2 = l.libdeflate_b200_device_malloc(ctx.h, 4 * n)
+        ctx._check(l.libdeflate_b200_crc32_batch(ctx.h, d_in.d_ptrs, d_in.d_sizes, None, d_c1, n), "crc")
+        ctx._check(l.libdeflate_b200_crc32_batch(ctx.h, d_out.d_ptrs, d_out.d_sizes, None, d_c2, n), "crc")
+        c1 = np.empty(n, dtype=np.uint32)
+        c2 = np.empty(n, dtype=np.uint32)
+        ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, c1.ctypes.data, d_c1, 4 * n), "d2h")
+        ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, c2.ctypes.data, d_c2, 4 * n), "d2h")
+        ctx.sync()
+        l.libdeflate_b200_device_free(ctx.h, d_c1)
+        l.libdeflate_b200_device_free(ctx.h, d_c2)
+        assert (c1 == c2).all(), "%s: round trip mismatch (device CRC of output != input)" % what
+        return c2
+
+    ref_ratio = None
+    csz_ref = None
+    if args.workload == "decompress":
+        csz_ref = load_reference_streams()
+        ref_ratio = float(csz_ref.sum()) / (n * chunk)
 
     def step():
         if args.workload == "roundtrip":
             ctx._check(l.libdeflate_b200_compress_batch(ctx.h, fmt, LEVEL, d_in.d_ptrs, d_in.d_sizes, d_comp.d_ptrs, d_comp.d_sizes, d_csz, n), "compress_batch")
-        ctx._check(l.libdeflate_b200_decompress_batch(ctx.h, fmt, 0, d_comp.d_ptrs, d_csz, d_out.d_ptrs, d_out.d_sizes, None, d_aout, d_res, n), "decompress_batch")
+        decompress_step(fmt)
 
-    # ---- kernel-path timing -----------------------------------------------------------
-    for _ in range(args.warmup):
-        step()
-    ctx.sync()
-    l.libdeflate_b200_ctx_set_profiling(ctx.h, 1)
-    l.libdeflate_b200_kernel_time_reset(ctx.h)
-    launches0 = ctx.launches
-    clocks = ClockSampler(local)
-    barrier()
-    ctx.sync()
-    if rank == 0:
-        clocks.start()
-    l.libdeflate_b200_timer_start(ctx.h)
-    for _ in range(args.steps):
-        step()
-    ms = l.libdeflate_b200_timer_stop_ms(ctx.h)
-    ctx.sync()
-    barrier()
-    clk = clocks.stop() if rank == 0 else None
-    launches = ctx.launches - launches0
-    ktime = {}
-    for name, k in KIND.items():
-        cnt = ctypes.c_uint64(0)
-        t = l.libdeflate_b200_kernel_time_ms(ctx.h, k, ctypes.byref(cnt))
-        ktime[name] = (t, cnt.value)
-    l.libdeflate_b200_ctx_set_profiling(ctx.h, 0)
+    # ---- kernel-path timing of the main workload --------------------------------------------
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms, ktime, launches, clk = timed_steps(ctx, l, step, args.steps, args.warmup, barrier, clocks)
     ms_max = max(allmax(ms), 1e-9)
 
     # ---- verification (outside the timed region) ----------------------------------------
-    res = np.empty(n, dtype=np.int32)
-    aout = np.empty(n, dtype=np.uint64)
+    c2 = check_outputs("main workload")
     csz = np.empty(n, dtype=np.uint64)
-    ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, res.ctypes.data, d_res, 4 * n), "d2h")
-    ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, aout.ctypes.data, d_aout, 8 * n), "d2h")
     ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, csz.ctypes.data, d_csz, 8 * n), "d2h")
     ctx.sync()
-    assert (res == 0).all(), "decompress verdicts not all SUCCESS: %s" % np.unique(res, return_counts=True)
-    assert (aout == chunk).all(), "decompressed sizes wrong"
     assert (csz > 0).all(), "a chunk did not fit its compress bound"
-    # checksum of checksums over every chunk (device CRC-32 of outputs vs inputs)
-    d_c1 = l.libdeflate_b200_device_malloc(ctx.h, 4 * n)
-    d_c2 = l.libdeflate_b200_device_malloc(ctx.h, 4 * n)
-    ctx._check(l.libdeflate_b200_crc32_batch(ctx.h, d_in.d_ptrs, d_in.d_sizes, None, d_c1, n), "crc")
-    ctx._check(l.libdeflate_b200_crc32_batch(ctx.h, d_out.d_ptrs, d_out.d_sizes, None, d_c2, n), "crc")
-    c1 = np.empty(n, dtype=np.uint32)
-    c2 = np.empty(n, dtype=np.uint32)
-    ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, c1.ctypes.data, d_c1, 4 * n), "d2h")
-    ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, c2.ctypes.data, d_c2, 4 * n), "d2h")
-    ctx.sync()
-    assert (c1 == c2).all(), "round trip mismatch (device CRC of output != input)"
     # bit-exact byte comparison with the host originals on every 64th chunk
     samp = np.arange(0, n, 64)
     host_in = np.ctypeslib.as_array(ctypes.cast(pin_in, ctypes.POINTER(ctypes.c_uint8)), shape=(n * chunk,))
@@ -402,6 +472,7 @@ def run_b200(args):
         assert np.array_equal(tmp, host_in[int(i) * chunk:(int(i) + 1) * chunk]), "byte mismatch in chunk %d" % i
         assert zlib.crc32(tmp.tobytes()) == int(c2[i]), "device CRC-32 disagrees with zlib on chunk %d" % i
     ratio = float(csz.sum()) / (n * chunk)
+    comp_bytes = float(csz.sum())
 
     # ---- e2e: host buffers through the public *_batch_host calls -------------------------
     e2e = None
@@ -411,11 +482,13 @@ def run_b200(args):
     # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload ------------
     cpu_baseline = None
     if rank == 0 and world == 1 and cpub is not None and not args.no_cpu:
-        ns = min(n, max(1024, 2048 * host_threads()))
-        tc, td, total, _ = cpu_roundtrip(cpub, 2 if args.workload == "roundtrip" else 0, LEVEL, pin_in, chunk, ns, host_threads())
+        ht = host_threads()
+        ns = min(n, max(1024, 2048 * ht))
+        tc, td, total, _ = cpu_roundtrip(cpub, 2 if args.workload == "roundtrip" else 0, LEVEL, pin_in, chunk, ns, ht)
         t = (tc + td) if args.workload == "roundtrip" else td
-        cpu_baseline = {"value": round(ns * chunk / 1e6 / t, 2), "unit": "MB/s", "cores": host_threads(), "host_cpus_online": os.cpu_count(), "cpu_quota": cpu_quota(), "kind": "reference",
-                        "sample": "first %d chunks of the same batch, one pass, oracle/_ref (unmodified libdeflate 1.25, -O2) on %d host threads" % (ns, host_threads()),
+        cpu_baseline = {"value": round(ns * chunk / 1e6 / t, 2), "unit": "MB/s", "cores": ht, "host_cpus_online": os.cpu_count(), "cpu_quota": cpu_quota(), "kind": "reference",
+                        "per_thread_MBps": round(ns * chunk / 1e6 / t / ht, 2),
+                        "sample": "first %d chunks of the same batch, one pass, oracle/_ref (unmodified libdeflate 1.25, -O2) on %d host threads" % (ns, ht),
                         "compress_MBps": round(ns * chunk / 1e6 / tc, 2), "decompress_MBps": round(ns * chunk / 1e6 / td, 2),
                         "ratio": round(total / float(ns * chunk), 4)}
         n1 = min(n, 256)
@@ -423,47 +496,125 @@ def run_b200(args):
         cpu_baseline["one_thread_compress_MBps"] = round(n1 * chunk / 1e6 / tc1, 2)
         cpu_baseline["one_thread_decompress_MBps"] = round(n1 * chunk / 1e6 / td1, 2)
 
-    # ---- report --------------------------------------------------------------------------
-    peak, peak_src = load_peaks()
+    # ---- rooflines of the main workload ----------------------------------------------------
     steps = args.steps
     total_unc = allsum(float(n * chunk))
     value = total_unc * steps / 1e6 / (ms_max / 1e3)
-    t_inf, n_inf = ktime["inflate"]
-    t_def, n_def = ktime["deflate"]
-    comp_bytes = float(csz.sum())
-    # algorithmic bytes per launch: inflate = compressed in + uncompressed out;
-    # deflate = uncompressed in + compressed out
-    alg_inf = comp_bytes + n * chunk
-    alg_def = n * chunk + comp_bytes
-    traffic_key = "%s_L%d_%dx%d" % (args.workload, LEVEL, n, chunk)
-    try:
-        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(traffic_key, {})
-    except Exception:
-        traffic_db = {}
+    # algorithmic bytes per launch: inflate = compressed in + uncompressed out over the
+    # decode + resolve pair; deflate = uncompressed in + compressed out
+    alg = n * chunk + comp_bytes
+    tkey = "%s_L%d_%dx%d" % (args.workload, LEVEL, n, chunk)
+    tdb = load_traffic(tkey)
+    INF = ["ldb_inflate_decode_kernel", "ldb_inflate_resolve_kernel"]
+    t_inf = ktime["inflate"][0] + ktime["resolve"][0]
+    r_inf = roofline_entry(INF, t_inf, ktime["inflate"][1], alg, tdb, tkey, peak, peak_src)
+    if r_inf:
+        r_inf["decode_ms"] = round(ktime["inflate"][0] / max(1, ktime["inflate"][1]), 4)
+        r_inf["resolve_ms"] = round(ktime["resolve"][0] / max(1, ktime["resolve"][1]), 4)
+    r_def = roofline_entry(["ldb_deflate_lz_kernel"], ktime["deflate"][0], ktime["deflate"][1], alg, tdb, tkey, peak, peak_src)
+    dominant = r_def if (r_def and ktime["deflate"][0] >= t_inf) else r_inf
 
-    def roof(t, cnt, alg, name):
-        if cnt == 0 or t <= 0:
-            return None
-        per = t / cnt / 1e3
-        ach = alg / per / 1e9
-        tr = traffic_db.get(name, {}).get("dram_bytes_per_launch")
-        return {"kernel": name, "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": int(tr) if tr else None,
-                "traffic_source": ("profiles/dram_traffic.json[%s] (ncu dram__bytes_read+write, same configuration)" % traffic_key) if tr else None,
-                "peak_source": peak_src,
-                "avg_launch_ms": round(per * 1e3, 4), "algorithmic_bytes_per_launch": int(alg)}
-    r_inf = roof(t_inf, n_inf, alg_inf, "ldb_inflate_kernel")
-    r_def = roof(t_def, n_def, alg_def, "ldb_deflate_lz_kernel")
-    dominant = r_def if (r_def and t_def >= t_inf) else r_inf
+    # ---- the other BASELINE configurations, short legs (N=1 only) ----------------------------
+    extra = None
+    if world == 1 and not args.no_extra and args.workload == "roundtrip" and chunk == CHUNK_DEFAULT:
+        extra = {}
+        # (configs[2]) raw DEFLATE decompress-only of the REFERENCE's L6 streams: the north-star roofline run
+        if cpub is not None:
+            cs = load_reference_streams()
+            k = max(3, min(args.steps, 10))
+            ms_d, kt_d, _, _ = timed_steps(ctx, l, lambda: decompress_step(ldb.RAW), k, 3)
+            check_outputs("decompress leg")
+            alg_d = n * chunk + float(cs.sum())
+            dkey = "decompress_L6_%dx%d" % (n, chunk)
+            rd = roofline_entry(INF, kt_d["inflate"][0] + kt_d["resolve"][0], kt_d["inflate"][1], alg_d, load_traffic(dkey), dkey, peak, peak_src)
+            if rd:
+                rd["decode_ms"] = round(kt_d["inflate"][0] / k, 4)
+                rd["resolve_ms"] = round(kt_d["resolve"][0] / k, 4)
+            leg = {"config": "configs[2]: %d x %d B raw DEFLATE decompress-only, the reference's own level-6 streams" % (n, chunk),
+                   "value": round(n * chunk * k / 1e6 / (ms_d / 1e3), 2), "unit": "MB/s", "steps": k, "warmup": 3, "ms_per_step": round(ms_d / k, 4),
+                   "ratio_reference_L6": round(float(cs.sum()) / (n * chunk), 4), "roofline": rd}
+            if rank == 0 and not args.no_cpu:
+                ht = host_threads()
+                ns = min(n, max(1024, 2048 * ht))
+                _, td, _, _ = cpu_roundtrip(cpub, 0, 6, pin_in, chunk, ns, ht)
+                leg["cpu_baseline"] = {"value": round(ns * chunk / 1e6 / td, 2), "unit": "MB/s", "cores": ht, "kind": "reference",
+                                       "per_thread_MBps": round(ns * chunk / 1e6 / td / ht, 2),
+                                       "sample": "first %d chunks, one raw-DEFLATE decompress pass of the reference on %d host threads" % (ns, ht)}
+            extra["decompress_reference_streams"] = leg
+            r_inf_north = rd
+        else:
+            r_inf_north = None
+        # standalone checksum kernels over the input batch
+        d_sum = l.libdeflate_b200_device_malloc(ctx.h, 4 * n)
+        for kind, fn in (("crc32", l.libdeflate_b200_crc32_batch), ("adler32", l.libdeflate_b200_adler32_batch)):
+            ms_c, kt_c, _, _ = timed_steps(ctx, l, lambda: ctx._check(fn(ctx.h, d_in.d_ptrs, d_in.d_sizes, None, d_sum, n), kind), 10, 3)
+            rc = roofline_entry(["ldb_%s_kernel" % kind], kt_c[kind][0], kt_c[kind][1], float(n * chunk), {}, "", peak, peak_src)
+            extra[kind] = {"config": "%d x %d B, one %s per chunk" % (n, chunk, kind), "value": round(n * chunk * 10 / 1e6 / (ms_c / 1e3), 2), "unit": "MB/s",
+                           "ms_per_step": round(ms_c / 10, 4), "roofline": rc}
+        l.libdeflate_b200_device_free(ctx.h, d_sum)
+        if cpub is not None and rank == 0 and not args.no_cpu:
+            ht = host_threads()
+            ns = min(n, 4096 * ht)
+            sums = (ctypes.c_uint32 * ns)()
+            for kind, isad in (("crc32", 0), ("adler32", 1)):
+                t = cpub.cpub_checksum(isad, pin_in, chunk, ns, sums, ht)
+                extra[kind]["cpu_baseline"] = {"value": round(ns * chunk / 1e6 / t, 2), "unit": "MB/s", "cores": ht, "kind": "reference"}
+        # (configs[3]) level 12, 4096 x 1 MiB: same bytes, 16 chunks fused into one
+        if not args.no_l12 and n * chunk >= getattr(args, "l12_min_bytes", 1 << 30):
+            n12, c12 = n * chunk >> 20, 1 << 20
+            b12 = (l.libdeflate_gzip_compress_bound(None, c12) + 15) & ~15
+            if n12 * b12 <= n * cstride:
+                v_in = DeviceBatch(ctx, n12, c12, d_in.slab)
+                v_in.set_sizes(np.full(n12, c12, dtype=np.uint64))
+                v_comp = DeviceBatch(ctx, n12, b12, d_comp.slab)
+                v_comp.set_sizes(np.full(n12, b12, dtype=np.uint64))
+                v_out = DeviceBatch(ctx, n12, c12, d_out.slab)
+                v_out.set_sizes(np.full(n12, c12, dtype=np.uint64))
+
+                def step12():
+                    ctx._check(l.libdeflate_b200_compress_batch(ctx.h, ldb.GZIP, 12, v_in.d_ptrs, v_in.d_sizes, v_comp.d_ptrs, v_comp.d_sizes, d_csz, n12), "compress_batch L12")
+                    ctx._check(l.libdeflate_b200_decompress_batch(ctx.h, ldb.GZIP, 0, v_comp.d_ptrs, d_csz, v_out.d_ptrs, v_out.d_sizes, None, d_aout, d_res, n12), "decompress_batch L12")
+                ms12, kt12, _, _ = timed_steps(ctx, l, step12, 1, 1)
+                res12 = np.empty(n12, dtype=np.int32)
+                cs12 = np.empty(n12, dtype=np.uint64)
+                ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, res12.ctypes.data, d_res, 4 * n12), "d2h")
+                ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, cs12.ctypes.data, d_csz, 8 * n12), "d2h")
+                ctx.sync()
+                assert (res12 == 0).all() and (cs12 > 0).all(), "level-12 leg failed"
+                # bytes: the 1 MiB views alias the 64 KiB batch, so output == input chunk for chunk
+                check_outputs("level-12 leg", verdicts=False)
+                alg12 = n12 * c12 + float(cs12.sum())
+                leg = {"config": "configs[3]: %d x %d B gzip level 12 compress + decompress" % (n12, c12),
+                       "value": round(n12 * c12 / 1e6 / (ms12 / 1e3), 2), "unit": "MB/s", "steps": 1, "warmup": 1, "ms_per_step": round(ms12, 2),
+                       "kernel_ms_per_step": {k: round(v[0], 3) for k, v in kt12.items() if v[1]},
+                       "ratio": round(float(cs12.sum()) / (n12 * c12), 4),
+                       "roofline": roofline_entry(["ldb_deflate_lz_kernel"], kt12["deflate"][0], kt12["deflate"][1], alg12, {}, "", peak, peak_src)}
+                if cpub is not None and rank == 0 and not args.no_cpu:
+                    ht = host_threads()
+                    ns = min(n12, max(ht, 16))
+                    hostbuf = ctypes.cast(pin_in, ctypes.POINTER(ctypes.c_uint8))
+                    comp = (ctypes.c_uint8 * (b12 * ns))()
+                    sizes = (ctypes.c_size_t * ns)()
+                    fails = ctypes.c_int(0)
+                    t = cpub.cpub_compress(2, 12, hostbuf, c12, ns, comp, b12, sizes, ht, ctypes.byref(fails))
+                    leg["cpu_baseline"] = {"compress_MBps": round(ns * c12 / 1e6 / t, 2), "cores": ht, "kind": "reference", "ratio": round(sum(sizes) / float(ns * c12), 4),
+                                           "sample": "first %d x 1 MiB chunks, one level-12 gzip compress pass of the reference on %d host threads" % (ns, ht)}
+                extra["level12_1MiB"] = leg
+                for v in (v_in, v_comp, v_out):
+                    v.free()
+    else:
+        r_inf_north = None
+
     line = {
         "metric": metric_name(args), "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
         "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms_max / steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args),
-        "roofline": dominant, "roofline_inflate": r_inf, "roofline_deflate": r_def,
+        "roofline": dominant, "roofline_inflate": r_inf_north or r_inf, "roofline_deflate": r_def,
         "kernel_ms_per_step": {k: round(v[0] / steps, 4) for k, v in ktime.items() if v[1]},
         "ratio": round(ratio, 4), "ratio_reference_L6": ref_ratio,
         "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        "extra": extra,
         "verified": "all %d chunks: verdict SUCCESS, size, device CRC-32(out)==CRC-32(in); %d chunks byte-compared + zlib CRC" % (n, min(256, len(samp))),
     }
     if rank == 0:
@@ -555,6 +706,8 @@ def main():
     ap.add_argument("--level", type=int, default=LEVEL, help="compression level (BASELINE configs[3] uses 12 with --chunk-size 1048576 --chunks 4096)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short legs of the other BASELINE configs (decompress-only, checksums, level 12)")
+    ap.add_argument("--no-l12", action="store_true", help="skip the level-12 4096 x 1 MiB leg")
     args = ap.parse_args()
     LEVEL = args.level
     if args.warmup < 3:
