@@ -78,7 +78,7 @@ LIBDEFLATEAPI double libdeflate_b200_timer_stop_ms(struct libdeflate_b200_ctx *c
  * events on the context's stream.  kernel_time_ms() synchronises, then returns the summed
  * duration (ms) and launch count of one kind since the last reset.
  * kind: 0 crc32, 1 adler32, 2 inflate decode (Huffman -> tokens), 3 trailer-verify, 4 deflate,
- *       5 inflate resolve (tokens -> bytes). */
+ *       5 inflate resolve (tokens -> bytes), 6 pack. */
 LIBDEFLATEAPI void   libdeflate_b200_ctx_set_profiling(struct libdeflate_b200_ctx *ctx, int on);
 LIBDEFLATEAPI double libdeflate_b200_kernel_time_ms(struct libdeflate_b200_ctx *ctx, int kind, uint64_t *n_launches);
 LIBDEFLATEAPI void   libdeflate_b200_kernel_time_reset(struct libdeflate_b200_ctx *ctx);
@@ -151,6 +151,31 @@ libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *ctx, int format,
 				    const void *const *h_in, const size_t *h_in_nbytes,
 				    void *const *h_out, const size_t *h_out_avail,
 				    size_t *h_out_nbytes, size_t n_chunks);
+
+/*
+ * Packed forms: the compressed side of the batch is ONE host buffer, chunk i at offset
+ * h_offsets[i] (16-byte aligned starts, h_offsets[n] = bytes used) -- the layout a chunk container
+ * wants (per-chunk offset table, ref: libdeflate.h:103-112, README.md:131-135) and the one that
+ * moves only the produced bytes over PCIe: the device packs the bound-sized slots before the copy.
+ * compress: 0, a CUDA error code, or -1 when out_avail is too small (h_offsets[n] = bytes needed;
+ * libdeflate_*_compress_bound() summed over the chunks + 16 n is always enough).
+ * decompress: as libdeflate_b200_decompress_batch_host, input chunk i = h_in_dense + h_in_offsets[i].
+ */
+LIBDEFLATEAPI int
+libdeflate_b200_compress_batch_host_packed(struct libdeflate_b200_ctx *ctx, int format, int level,
+					   const void *const *h_in, const size_t *h_in_nbytes, size_t n_chunks,
+					   void *h_out, size_t out_avail, uint64_t *h_offsets, size_t *h_out_nbytes);
+LIBDEFLATEAPI int
+libdeflate_b200_decompress_batch_host_packed(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
+					     const void *h_in_dense, const uint64_t *h_in_offsets,
+					     const size_t *h_in_nbytes, size_t n_chunks,
+					     void *const *h_out, const size_t *h_out_avail,
+					     size_t *h_actual_in, size_t *h_actual_out, int32_t *h_results);
+/* Device-side packing (asynchronous): chunk i -> d_dense + d_offsets[i]; d_offsets has n + 1 entries,
+ * the last one is the packed size; chunks that would not fit dense_avail are skipped. */
+LIBDEFLATEAPI int
+libdeflate_b200_pack_batch(struct libdeflate_b200_ctx *ctx, const void *const *d_ptrs, const size_t *d_sizes,
+			   size_t n_chunks, void *d_dense, size_t dense_avail, uint64_t *d_offsets);
 
 /*
  * One large buffer <-> a blocked gzip file (BGZF: RFC 1952 members of at most

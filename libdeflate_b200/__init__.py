@@ -46,6 +46,7 @@ BATCH_SYMBOLS = [
     "libdeflate_b200_decompress_batch", "libdeflate_b200_compress_batch",
     "libdeflate_b200_crc32_batch", "libdeflate_b200_adler32_batch",
     "libdeflate_b200_decompress_batch_host", "libdeflate_b200_compress_batch_host",
+    "libdeflate_b200_decompress_batch_host_packed", "libdeflate_b200_compress_batch_host_packed", "libdeflate_b200_pack_batch",
     "libdeflate_b200_bgzf_compress_bound", "libdeflate_b200_bgzf_compress", "libdeflate_b200_bgzf_decompress",
 ]
 
@@ -144,6 +145,12 @@ def load_library(path=None):
     lib.libdeflate_b200_decompress_batch_host.argtypes = [P, c_int, c_uint, P, P, P, P, P, P, P, S]
     lib.libdeflate_b200_compress_batch_host.restype = c_int
     lib.libdeflate_b200_compress_batch_host.argtypes = [P, c_int, c_int, P, P, P, P, P, S]
+    lib.libdeflate_b200_compress_batch_host_packed.restype = c_int
+    lib.libdeflate_b200_compress_batch_host_packed.argtypes = [P, c_int, c_int, P, P, S, P, S, P, P]
+    lib.libdeflate_b200_decompress_batch_host_packed.restype = c_int
+    lib.libdeflate_b200_decompress_batch_host_packed.argtypes = [P, c_int, c_uint, P, P, P, S, P, P, P, P, P]
+    lib.libdeflate_b200_pack_batch.restype = c_int
+    lib.libdeflate_b200_pack_batch.argtypes = [P, P, P, S, P, S, P]
     lib.libdeflate_b200_bgzf_compress_bound.restype = S
     lib.libdeflate_b200_bgzf_compress_bound.argtypes = [S]
     lib.libdeflate_b200_bgzf_compress.restype = c_int
@@ -306,6 +313,51 @@ class Context:
         for i in range(n):
             out.append(slab.raw[off:off + res[i]] if res[i] else None)
             off += avail[i]
+        return out
+
+    def compress_batch_host_packed(self, chunks, level=6, fmt=RAW, out_avail=None):
+        """(packed bytes, offsets[n + 1], sizes[n]) -- chunk i is packed[offsets[i]:offsets[i] + sizes[i]];
+        None when out_avail was too small."""
+        n = len(chunks)
+        ptrs, sizes, keep = self._host_arrays(chunks)
+        bound = getattr(self.l, "libdeflate_%s_compress_bound" % ("deflate", "zlib", "gzip")[fmt])
+        avail = sum(bound(None, len(c)) + 16 for c in chunks) if out_avail is None else out_avail
+        out = ctypes.create_string_buffer(max(avail, 1))
+        offs = (ctypes.c_uint64 * (n + 1))()
+        osz = (c_size_t * n)()
+        rc = self.l.libdeflate_b200_compress_batch_host_packed(self.h, fmt, level, ptrs, sizes, n, out, avail, offs, osz)
+        if rc == -1:
+            return None
+        self._check(rc, "compress_batch_host_packed")
+        return out.raw[:offs[n]], list(offs), list(osz)
+
+    def decompress_batch_host_packed(self, packed, offsets, sizes, out_avail, fmt=RAW, exact=False):
+        """Like decompress_batch_host, the streams being packed[offsets[i]:offsets[i] + sizes[i]]."""
+        n = len(sizes)
+        if isinstance(out_avail, int):
+            out_avail = [out_avail] * n
+        offs = (ctypes.c_uint64 * max(n, 1))(*offsets[:n])
+        isz = (c_size_t * max(n, 1))(*sizes)
+        slab = ctypes.create_string_buffer(max(sum(out_avail), 1))
+        optrs = (c_void_p * max(n, 1))()
+        osz = (c_size_t * max(n, 1))()
+        off = 0
+        base = ctypes.addressof(slab)
+        for i in range(n):
+            optrs[i] = base + off
+            osz[i] = out_avail[i]
+            off += out_avail[i]
+        ain = (c_size_t * max(n, 1))()
+        aout = (c_size_t * max(n, 1))()
+        res = (c_int32 * max(n, 1))()
+        self._check(self.l.libdeflate_b200_decompress_batch_host_packed(
+            self.h, fmt, EXACT_OUT_SIZE if exact else 0, packed, offs, isz, n, optrs, osz, ain, aout, res), "decompress_batch_host_packed")
+        out = []
+        off = 0
+        raw = slab.raw
+        for i in range(n):
+            out.append((SUCCESS, raw[off:off + aout[i]], ain[i], aout[i]) if res[i] == SUCCESS else (res[i], None, 0, 0))
+            off += out_avail[i]
         return out
 
     def bgzf_compress(self, data, level=6, out_avail=None):

@@ -133,6 +133,10 @@ int ldb_inflate_grid_blocks(const ldb_launch_cfg &cfg);
 size_t ldb_inflate_scratch_bytes(const ldb_launch_cfg &cfg, size_t n);
 int ldb_launch_verify_trailer(const ldb_inflate_args &a, const u32 *d_checksums, void *stream);
 
+// pack_kernels.cu: chunk i -> d_dense + d_offsets[i], offsets = prefix sums of the sizes rounded up to 16
+int ldb_launch_pack(const void *const *d_ptrs, const size_t *d_sizes, size_t n, void *d_dense, size_t dense_avail,
+		    u64 *d_offsets, const ldb_launch_cfg &cfg, void *stream);
+
 struct ldb_deflate_args {
 	const void *const *in_ptrs;
 	const size_t *in_nbytes;

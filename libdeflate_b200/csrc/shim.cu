@@ -113,7 +113,7 @@ struct ldb_buf {
 };
 
 // kernel kinds for libdeflate_b200_kernel_time_ms()
-enum { LDB_K_CRC32 = 0, LDB_K_ADLER32 = 1, LDB_K_INFLATE = 2, LDB_K_VERIFY = 3, LDB_K_DEFLATE = 4, LDB_K_RESOLVE = 5, LDB_KERNEL_KINDS = 6 };
+enum { LDB_K_CRC32 = 0, LDB_K_ADLER32 = 1, LDB_K_INFLATE = 2, LDB_K_VERIFY = 3, LDB_K_DEFLATE = 4, LDB_K_RESOLVE = 5, LDB_K_PACK = 6, LDB_KERNEL_KINDS = 7 };
 struct ldb_prof_rec {
 	cudaEvent_t a, b;
 	int kind;
@@ -129,6 +129,7 @@ struct libdeflate_b200_ctx {
 	ldb_buf deflate_scratch;	// device
 	ldb_buf tmp;			// device: per-batch u32/size_t arrays
 	ldb_buf d_stage_in, d_stage_out;// device staging for host-buffer calls
+	ldb_buf d_pack;			// device: packed output of the *_packed host calls
 	ldb_buf d_params;		// device: pointer/size arrays for host-buffer calls
 	ldb_buf h_pinned;		// pinned host staging
 	u64 launches;
@@ -249,6 +250,7 @@ extern "C" void libdeflate_b200_ctx_destroy(struct libdeflate_b200_ctx *ctx)
 	cudaFree(ctx->tmp.p);
 	cudaFree(ctx->d_stage_in.p);
 	cudaFree(ctx->d_stage_out.p);
+	cudaFree(ctx->d_pack.p);
 	cudaFree(ctx->d_params.p);
 	if (ctx->h_pinned.p) cudaFreeHost(ctx->h_pinned.p);
 	delete ctx;
@@ -570,12 +572,14 @@ struct host_span {
 	bool compact;
 };
 
-// If the host chunks sit back to back or in regular slots of one allocation, the whole span is
-// moved with a single copy and device pointers are base + (h_ptr - lo).  For output
-// buffers the span is copied BACK over host memory, so 'exact' demands that the
-// buffers tile the span with no gaps at all (nothing that is not the caller's
-// output buffer may be overwritten).
-static host_span span_of(const void *const *ptrs, const size_t *sizes, size_t n, bool exact)
+// If the host chunks sit back to back, the whole span is moved with a single copy and device
+// pointers are base + (h_ptr - lo).  "Back to back" is checked, never assumed: a span with gaps
+// is only read or written as a whole when the caller has DECLARED it one allocation ('one_alloc':
+// the *_packed entry points, whose chunks live inside one caller buffer by construction) -- the
+// bytes between independently allocated buffers are not ours to touch (they may not even be
+// mapped).  For output buffers the span is copied BACK over host memory, so they must tile it
+// exactly in every case.
+static host_span span_of(const void *const *ptrs, const size_t *sizes, size_t n, bool exact, bool one_alloc = false)
 {
 	host_span s{nullptr, nullptr, 0, false};
 	bool tiled = true;
@@ -588,10 +592,10 @@ static host_span span_of(const void *const *ptrs, const size_t *sizes, size_t n,
 		s.sum += sizes[i];
 	}
 	if (s.lo) {
-		if (exact) s.compact = tiled && (size_t)(s.hi - s.lo) == s.sum;
-		// inputs: gaps are simply transferred too as long as the span stays within 4x the payload
-		// (e.g. streams sitting in compress_bound()-sized slots); one DMA beats n small ones
-		else s.compact = (size_t)(s.hi - s.lo) <= 4 * s.sum + 64 * n + 4096;
+		s.compact = tiled && (size_t)(s.hi - s.lo) == s.sum;
+		// gaps inside ONE declared allocation are simply transferred too as long as the span stays
+		// within 4x the payload (e.g. 16-byte aligned packing); one DMA beats n small ones
+		if (!exact && one_alloc && (size_t)(s.hi - s.lo) <= 4 * s.sum + 64 * n + 4096) s.compact = true;
 	}
 	return s;
 }
@@ -608,9 +612,9 @@ struct staged_batch {
 // Lays out n buffers of the given sizes in a device slab (16-byte aligned each, or
 // mirroring the host span when compact) and uploads pointer + size arrays.
 static int stage_layout(libdeflate_b200_ctx *ctx, ldb_buf &slab, const void *const *h_ptrs, const size_t *h_sizes,
-			size_t n, bool copy_in, bool exact, u8 *param_base_d, u8 *param_base_h, staged_batch *sb)
+			size_t n, bool copy_in, bool exact, u8 *param_base_d, u8 *param_base_h, staged_batch *sb, bool one_alloc = false)
 {
-	host_span sp = span_of(h_ptrs, h_sizes, n, exact);
+	host_span sp = span_of(h_ptrs, h_sizes, n, exact, one_alloc);
 	sb->compact = sp.compact;
 	sb->offsets = (size_t *)malloc(n * sizeof(size_t) + 8);
 	size_t total = 0;
@@ -675,11 +679,11 @@ static bool host_ordered(const void *const *ptrs, const size_t *sizes, size_t n)
 }
 
 static bool pipeline_eligible(const libdeflate_b200_ctx *ctx, const void *const *h_in, const size_t *in_sz,
-			      const void *const *h_out, const size_t *out_sz, size_t n)
+			      const void *const *h_out, const size_t *out_sz, size_t n, bool in_one_alloc = false)
 {
 	if (n < LDB_PIPE_MIN_CHUNKS || !ctx->stream_h2d || !ctx->stream_d2h) return false;
 	if (getenv("LIBDEFLATE_B200_NO_PIPELINE")) return false;
-	host_span a = span_of(h_in, in_sz, n, false), b = span_of(h_out, out_sz, n, true);
+	host_span a = span_of(h_in, in_sz, n, false, in_one_alloc), b = span_of(h_out, out_sz, n, true);
 	return a.compact && b.compact && host_ordered(h_in, in_sz, n) && host_ordered(h_out, out_sz, n);
 }
 
@@ -716,11 +720,11 @@ static size_t pipe_stages(size_t n, size_t total_bytes, size_t min_chunks)
 	return s;
 }
 
-extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
-						      const void *const *h_in, const size_t *h_in_nbytes,
-						      void *const *h_out, const size_t *h_out_avail,
-						      size_t *h_actual_in, size_t *h_actual_out,
-						      int32_t *h_results, size_t n)
+static int ldb_decompress_batch_host_impl(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
+					  const void *const *h_in, const size_t *h_in_nbytes,
+					  void *const *h_out, const size_t *h_out_avail,
+					  size_t *h_actual_in, size_t *h_actual_out,
+					  int32_t *h_results, size_t n, bool in_one_alloc)
 {
 	if (n == 0) return 0;
 	cudaSetDevice(ctx->device);
@@ -734,9 +738,9 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 	u8 *hparam = (u8 *)hparam_own.p;
 	if (!hparam) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
 	u8 *dparam = (u8 *)ctx->d_params.p;
-	const bool pipelined = pipeline_eligible(ctx, h_in, h_in_nbytes, (const void *const *)h_out, h_out_avail, n);
+	const bool pipelined = pipeline_eligible(ctx, h_in, h_in_nbytes, (const void *const *)h_out, h_out_avail, n, in_one_alloc);
 	staged_batch in_sb{}, out_sb{};
-	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, !pipelined, false, dparam, hparam, &in_sb);
+	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, !pipelined, false, dparam, hparam, &in_sb, in_one_alloc);
 	if (!rc) rc = stage_layout(ctx, ctx->d_stage_out, (const void *const *)h_out, h_out_avail, n, false, true, dparam + pb, hparam + pb, &out_sb);
 	if (!rc) rc = cudaMemcpyAsync(dparam, hparam, 2 * pb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "H2D params", __FILE__, __LINE__);
 	size_t *d_ain = (size_t *)(dparam + res_off);
@@ -744,7 +748,7 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 	s32 *d_res = (s32 *)(dparam + res_off + 2 * align_up(n * sizeof(size_t), 256));
 	bool out_copied = false;
 	if (!rc && pipelined) {
-		host_span isp = span_of(h_in, h_in_nbytes, n, false), osp = span_of((const void *const *)h_out, h_out_avail, n, true);
+		host_span isp = span_of(h_in, h_in_nbytes, n, false, in_one_alloc), osp = span_of((const void *const *)h_out, h_out_avail, n, true);
 		const size_t imis = (uintptr_t)isp.lo & 15, omis = (uintptr_t)osp.lo & 15;
 		const size_t S = pipe_stages(n, (size_t)(isp.hi - isp.lo) + (size_t)(osp.hi - osp.lo), 16384);
 		pipe_events ev;
@@ -804,6 +808,159 @@ extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx 
 		}
 	}
 	return rc;
+}
+
+extern "C" int libdeflate_b200_decompress_batch_host(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
+						      const void *const *h_in, const size_t *h_in_nbytes,
+						      void *const *h_out, const size_t *h_out_avail,
+						      size_t *h_actual_in, size_t *h_actual_out,
+						      int32_t *h_results, size_t n)
+{
+	return ldb_decompress_batch_host_impl(ctx, format, flags, h_in, h_in_nbytes, h_out, h_out_avail,
+					      h_actual_in, h_actual_out, h_results, n, false);
+}
+
+// Packed input: the n streams live in ONE caller buffer, chunk i at h_in_dense + h_in_offsets[i]
+// (e.g. what libdeflate_b200_compress_batch_host_packed wrote).  Because the caller vouches for the
+// whole buffer, it crosses PCIe in one piece per sub-batch, gaps (alignment padding) included.
+extern "C" int libdeflate_b200_decompress_batch_host_packed(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
+							     const void *h_in_dense, const uint64_t *h_in_offsets,
+							     const size_t *h_in_nbytes, size_t n,
+							     void *const *h_out, const size_t *h_out_avail,
+							     size_t *h_actual_in, size_t *h_actual_out, int32_t *h_results)
+{
+	if (n == 0) return 0;
+	host_scratch ptrs_own(n * sizeof(void *));
+	const void **ptrs = (const void **)ptrs_own.p;
+	if (!ptrs) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
+	for (size_t i = 0; i < n; i++) ptrs[i] = (const u8 *)h_in_dense + h_in_offsets[i];
+	return ldb_decompress_batch_host_impl(ctx, format, flags, ptrs, h_in_nbytes, h_out, h_out_avail,
+					      h_actual_in, h_actual_out, h_results, n, true);
+}
+
+// Device-side packing of a batch (pack_kernels.cu): asynchronous; d_offsets[n] is the packed size.
+extern "C" int libdeflate_b200_pack_batch(struct libdeflate_b200_ctx *ctx, const void *const *d_ptrs, const size_t *d_sizes,
+					   size_t n, void *d_dense, size_t dense_avail, uint64_t *d_offsets)
+{
+	if (n == 0) return 0;
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
+	ctx->launches++;	// offsets + copy
+	return ldb_timed_launch(ctx, LDB_K_PACK, [&] { return ldb_launch_pack(d_ptrs, d_sizes, n, d_dense, dense_avail, (u64 *)d_offsets, ctx->cfg, ctx->stream); });
+}
+
+static size_t bound_of(int format, size_t n)
+{
+	size_t blocks = (n + 4999) / 5000;
+	if (blocks < 1) blocks = 1;
+	return 5 * blocks + n + (format == LDB_FMT_GZIP ? 18 : (format == LDB_FMT_ZLIB ? 6 : 0));
+}
+
+// Packed output: chunk i is written to h_out + h_offsets[i] (16-byte aligned starts, h_offsets[n] =
+// bytes used), h_out_nbytes[i] = its size (0: input too large for its compress bound -- cannot
+// happen).  The batch is compressed into bound-sized device slots, packed on the device, and only
+// the packed bytes cross PCIe.  Returns 0, a CUDA error code, or -1 when out_avail is too small
+// (h_offsets[n] then tells how much is needed; nothing useful is in h_out).
+extern "C" int libdeflate_b200_compress_batch_host_packed(struct libdeflate_b200_ctx *ctx, int format, int level,
+							   const void *const *h_in, const size_t *h_in_nbytes, size_t n,
+							   void *h_out, size_t out_avail, uint64_t *h_offsets, size_t *h_out_nbytes)
+{
+	if (h_offsets) h_offsets[0] = 0;
+	if (n == 0) return 0;
+	if (format < LDB_FMT_RAW || format > LDB_FMT_GZIP) return ldb_fail(cudaErrorInvalidValue, "format", __FILE__, __LINE__);
+	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
+	// device slots: one per chunk, compress_bound() rounded up to 16
+	host_scratch slot_own((n + 1) * sizeof(size_t));
+	size_t *slot_off = (size_t *)slot_own.p;
+	if (!slot_off) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
+	size_t slots = 0;
+	for (size_t i = 0; i < n; i++) {
+		slot_off[i] = slots;
+		slots += align_up(bound_of(format, h_in_nbytes[i]), 16);
+	}
+	slot_off[n] = slots;
+	// parameter block: in ptrs/sizes | out ptrs/avail | out sizes | offsets (n + 1 u64, per sub-batch)
+	const size_t pb = param_block_bytes(n);
+	const size_t sz_off = 2 * pb, off_off = sz_off + align_up(n * sizeof(size_t), 256);
+	const size_t par_bytes = off_off + align_up((n + LDB_PIPE_MAX_STAGES + 1) * sizeof(u64), 256);
+	int rc = ldb_reserve_dev(ctx->d_params, par_bytes);
+	if (rc) return rc;
+	host_scratch hparam_own(par_bytes);
+	u8 *hparam = (u8 *)hparam_own.p;
+	if (!hparam) return ldb_fail(cudaErrorMemoryAllocation, "malloc", __FILE__, __LINE__);
+	u8 *dparam = (u8 *)ctx->d_params.p;
+	rc = ldb_reserve_dev(ctx->d_stage_out, slots + 64);
+	if (!rc) rc = ldb_reserve_dev(ctx->d_pack, slots + 64);
+	if (rc) return rc;
+	const bool pipelined = n >= LDB_PIPE_MIN_CHUNKS && ctx->stream_h2d && ctx->stream_d2h && !getenv("LIBDEFLATE_B200_NO_PIPELINE") &&
+			       span_of(h_in, h_in_nbytes, n, false).compact && host_ordered(h_in, h_in_nbytes, n);
+	staged_batch in_sb{};
+	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, !pipelined, false, dparam, hparam, &in_sb);
+	if (rc) return rc;
+	void **hop = (void **)(hparam + pb);
+	size_t *hos = (size_t *)(hparam + pb + align_up(n * sizeof(void *), 256));
+	for (size_t i = 0; i < n; i++) {
+		hop[i] = (u8 *)ctx->d_stage_out.p + slot_off[i];
+		hos[i] = slot_off[i + 1] - slot_off[i];
+	}
+	LDB_CUDA_CHECK_RET(cudaMemcpyAsync(dparam, hparam, 2 * pb, cudaMemcpyHostToDevice, ctx->stream));
+	void **d_op = (void **)(dparam + pb);
+	size_t *d_os = (size_t *)(dparam + pb + align_up(n * sizeof(void *), 256));
+	size_t *d_on = (size_t *)(dparam + sz_off);
+	u64 *d_offs = (u64 *)(dparam + off_off);
+	u64 *r_offs = (u64 *)(hparam + off_off);
+	size_t *r_on = (size_t *)(hparam + sz_off);
+
+	const size_t S = pipelined ? pipe_stages(n, in_sb.slab_bytes + slots / 3, 1024) : 1;
+	pipe_events ev;
+	rc = pipe_events_create(&ev, (int)S);
+	if (rc) return rc;
+	host_span isp = span_of(h_in, h_in_nbytes, n, false);
+	const size_t imis = (uintptr_t)isp.lo & 15;
+	u64 host_pos = 0;	// bytes of h_out used so far
+	bool too_small = false;
+	// sub-batch k: H2D -> compress -> pack -> offsets/sizes D2H; its packed bytes are fetched while
+	// sub-batch k + 1 is being compressed
+	auto fetch = [&](size_t k) -> int {
+		const size_t i0 = n * k / S, i1 = n * (k + 1) / S;
+		LDB_CUDA_CHECK_RET(cudaEventSynchronize(ev.done[k]));
+		const u64 *lo = r_offs + i0 + k;	// this sub-batch's n_k + 1 offsets
+		const u64 total = lo[i1 - i0];
+		for (size_t i = i0; i < i1; i++) {
+			h_offsets[i] = host_pos + lo[i - i0];
+			h_out_nbytes[i] = r_on[i];
+		}
+		if (host_pos + total > out_avail) too_small = true;
+		else if (total) LDB_CUDA_CHECK_RET(cudaMemcpyAsync((u8 *)h_out + host_pos, (u8 *)ctx->d_pack.p + slot_off[i0], (size_t)total, cudaMemcpyDeviceToHost,
+								    pipelined ? ctx->stream_d2h : ctx->stream));
+		host_pos += total;
+		h_offsets[i1] = host_pos;
+		return 0;
+	};
+	for (size_t k = 0; k < S; k++) {
+		const size_t i0 = n * k / S, i1 = n * (k + 1) / S;
+		if (pipelined) {
+			const u8 *ilo = (const u8 *)h_in[i0], *ihi = (const u8 *)h_in[i1 - 1] + h_in_nbytes[i1 - 1];
+			if (ihi > ilo) LDB_CUDA_CHECK_RET(cudaMemcpyAsync(in_sb.d_base + imis + (ilo - isp.lo), ilo, (size_t)(ihi - ilo), cudaMemcpyHostToDevice, ctx->stream_h2d));
+			LDB_CUDA_CHECK_RET(cudaEventRecord(ev.in[k], ctx->stream_h2d));
+			LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream, ev.in[k], 0));
+		}
+		rc = libdeflate_b200_compress_batch(ctx, format, level, (const void *const *)in_sb.d_ptrs + i0, in_sb.d_sizes + i0,
+						    (void *const *)d_op + i0, d_os + i0, d_on + i0, i1 - i0);
+		if (rc) return rc;
+		rc = libdeflate_b200_pack_batch(ctx, (const void *const *)d_op + i0, d_on + i0, i1 - i0, (u8 *)ctx->d_pack.p + slot_off[i0],
+						slot_off[i1] - slot_off[i0], d_offs + i0 + k);
+		if (rc) return rc;
+		LDB_CUDA_CHECK_RET(cudaMemcpyAsync(r_offs + i0 + k, d_offs + i0 + k, (i1 - i0 + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+		LDB_CUDA_CHECK_RET(cudaMemcpyAsync(r_on + i0, d_on + i0, (i1 - i0) * sizeof(size_t), cudaMemcpyDeviceToHost, ctx->stream));
+		LDB_CUDA_CHECK_RET(cudaEventRecord(ev.done[k], ctx->stream));
+		if (pipelined) LDB_CUDA_CHECK_RET(cudaStreamWaitEvent(ctx->stream_d2h, ev.done[k], 0));
+		if (k > 0) { rc = fetch(k - 1); if (rc) return rc; }
+	}
+	rc = fetch(S - 1);
+	if (rc) return rc;
+	LDB_CUDA_CHECK_RET(cudaStreamSynchronize(pipelined ? ctx->stream_d2h : ctx->stream));
+	LDB_CUDA_CHECK_RET(cudaStreamSynchronize(ctx->stream));
+	return too_small ? -1 : 0;
 }
 
 extern "C" int libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *ctx, int format, int level,

@@ -89,6 +89,70 @@ def check_decompress_large(ctx, sizes=(150000, 262144 + 123), levels=(0, 1, 6, 9
             assert g[0] == 0 and g[3] == len(p) and g[1] == p, ("large chunk mismatch", lv, len(p), g[0])
 
 
+def check_packed_round_trip(ctx, n_chunks=300, seed=9, fmts=(0, 2), level=6):
+    """The packed host forms: offsets are 16-byte aligned and ascending, the packed streams equal what the
+    unpacked call produces, a too small buffer is reported (not overrun), and the packed decompress call
+    returns the inputs."""
+    rng = random.Random(seed)
+    chunks = [corpus.text(rng.choice([0, 1, 100, 3000, 20000, 65536]), i) if i % 3 else corpus.mixed(rng.randrange(1, 30000), i) for i in range(n_chunks)]
+    for fmt in fmts:
+        packed, offs, sizes = ctx.compress_batch_host_packed(chunks, level, fmt)
+        plain = ctx.compress_batch_host(chunks, level, fmt)
+        assert len(offs) == n_chunks + 1 and offs[0] == 0 and offs[-1] == len(packed)
+        for i, c in enumerate(chunks):
+            assert offs[i] % 16 == 0 and offs[i] + sizes[i] <= offs[i + 1] <= offs[i] + sizes[i] + 15
+            assert packed[offs[i]:offs[i] + sizes[i]] == plain[i], ("packed stream differs", fmt, i)
+        assert ctx.compress_batch_host_packed(chunks, level, fmt, out_avail=len(packed) - 1) is None
+        got = ctx.decompress_batch_host_packed(packed, offs, sizes, [len(c) for c in chunks], fmt)
+        for g, c in zip(got, chunks):
+            assert g[0] == 0 and g[1] == c
+    assert ctx.compress_batch_host_packed([], level, 0)[1] == [0]
+
+
+def check_inputs_with_unmapped_gaps(ctx):
+    """Independently allocated input buffers with an unmapped page between them: the host forms must read
+    the buffers they were given and nothing else (a whole-span copy would fault)."""
+    import ctypes
+    import mmap
+    page = mmap.PAGESIZE
+    m = mmap.mmap(-1, 5 * page)
+    base = ctypes.addressof(ctypes.c_char.from_buffer(m))
+    libc = ctypes.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    a = corpus.text(page, 1)
+    b = corpus.text(page, 2)
+    m[0:page] = a
+    m[2 * page:3 * page] = b
+    assert libc.mprotect(base + page, page, 0) == 0      # PROT_NONE between the two buffers
+    assert libc.mprotect(base + 3 * page, 2 * page, 0) == 0
+    try:
+        n = 2
+        ptrs = (ctypes.c_void_p * n)(base, base + 2 * page)
+        sizes = (ctypes.c_size_t * n)(page, page)
+        bound = ctx.l.libdeflate_gzip_compress_bound(None, page)
+        out = ctypes.create_string_buffer(2 * bound)
+        optrs = (ctypes.c_void_p * n)(ctypes.addressof(out), ctypes.addressof(out) + bound)
+        osz = (ctypes.c_size_t * n)(bound, bound)
+        res = (ctypes.c_size_t * n)()
+        ctx._check(ctx.l.libdeflate_b200_compress_batch_host(ctx.h, 2, 6, ptrs, sizes, optrs, osz, res, n), "compress_batch_host")
+        z = [out.raw[:res[0]], out.raw[bound:bound + res[1]]]
+        assert zlib.decompress(z[0], 31) == a and zlib.decompress(z[1], 31) == b
+        # and the same layout on the input side of decompress
+        m[0:len(z[0])] = z[0]
+        m[2 * page:2 * page + len(z[1])] = z[1]
+        isz = (ctypes.c_size_t * n)(len(z[0]), len(z[1]))
+        dst = ctypes.create_string_buffer(2 * page)
+        dptrs = (ctypes.c_void_p * n)(ctypes.addressof(dst), ctypes.addressof(dst) + page)
+        dav = (ctypes.c_size_t * n)(page, page)
+        rr = (ctypes.c_int32 * n)()
+        ao = (ctypes.c_size_t * n)()
+        ctx._check(ctx.l.libdeflate_b200_decompress_batch_host(ctx.h, 2, 0, ptrs, isz, dptrs, dav, None, ao, rr, n), "decompress_batch_host")
+        assert list(rr) == [0, 0] and dst.raw == a + b
+    finally:
+        libc.mprotect(base + page, page, 3)
+        libc.mprotect(base + 3 * page, 2 * page, 3)
+
+
 def fuzz_cases(n_cases, seed, max_size=20000):
     rng = random.Random(seed)
     base = []
@@ -200,6 +264,21 @@ def check_host_pipeline(library, ctx, n=2304, chunk=4096):
                                                        oav.ctypes.data, None, aout.ctypes.data, res.ctypes.data, n)
     assert rc == 0 and (res == 0).all() and (aout == chunk).all()
     assert out.tobytes() == raw
+    # the packed forms take the same sub-batched path: same streams, offsets consistent, round trip exact
+    packed = np.zeros(n * (bound + 16), dtype=np.uint8)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    psz = np.zeros(n, dtype=np.uint64)
+    rc = library.libdeflate_b200_compress_batch_host_packed(ctx.h, 2, 6, ip.ctypes.data, isz.ctypes.data, n, packed.ctypes.data,
+                                                            packed.size, offs.ctypes.data, psz.ctypes.data)
+    assert rc == 0 and (psz == csz).all() and (offs[:-1] % 16 == 0).all() and (np.diff(offs) >= psz).all() and (np.diff(offs) < psz + 16).all()
+    for i in (0, 1, n // 2, n - 1):
+        assert packed[int(offs[i]):int(offs[i]) + int(psz[i])].tobytes() == comp[i * bound:i * bound + int(csz[i])].tobytes()
+    out2 = np.zeros(n * chunk, dtype=np.uint8)
+    op2 = (out2.ctypes.data + idx * chunk).astype(np.uint64)
+    res[:] = -1
+    rc = library.libdeflate_b200_decompress_batch_host_packed(ctx.h, 2, 0, packed.ctypes.data, offs.ctypes.data, psz.ctypes.data, n,
+                                                              op2.ctypes.data, oav.ctypes.data, None, aout.ctypes.data, res.ctypes.data)
+    assert rc == 0 and (res == 0).all() and out2.tobytes() == raw
 
 
 def boundary_chunks():

@@ -90,5 +90,13 @@ def test_inflate_output_primitives_unit():
     assert subprocess.run([exe]).returncode == 0
 
 
+def test_packed_host_forms_emulated(emu_ctx):
+    pc.check_packed_round_trip(emu_ctx, n_chunks=60)
+
+
+def test_host_inputs_with_unmapped_gaps_emulated(emu_ctx):
+    pc.check_inputs_with_unmapped_gaps(emu_ctx)
+
+
 def test_pipelined_host_path_emulated(emu, emu_ctx):
     pc.check_host_pipeline(emu, emu_ctx)

@@ -66,6 +66,14 @@ def test_decompress_1mib_chunks(gpu_ctx, oracle):
         assert g[0] == 0 and g[1] == p
 
 
+def test_packed_host_forms(gpu_ctx):
+    pc.check_packed_round_trip(gpu_ctx, n_chunks=3000, fmts=(0, 1, 2))
+
+
+def test_host_inputs_with_unmapped_gaps(gpu_ctx):
+    pc.check_inputs_with_unmapped_gaps(gpu_ctx)
+
+
 def test_decompress_large_chunks(gpu_ctx):
     pc.check_decompress_large(gpu_ctx)
 
