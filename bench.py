@@ -251,7 +251,7 @@ def workload_config(args, n_override=None):
     return {"workload": w, "chunks_per_gpu": n, "chunk_bytes": args.chunk_size, "level": LEVEL,
             "format": "raw" if args.workload == "decompress" else "gzip",
             "l2_policy": "inputs (%.1f GiB per GPU) are far larger than the 126 MB L2; no explicit flush" % (n * args.chunk_size / 2.0**30),
-            "parallelism": "independent chunk shards per GPU, no data-path collective"}
+            "parallelism": "independent chunk shards per GPU, no data-path collective (the single-origin NCCL scatter/gather run of the same batch is reported under single_origin when N > 1)"}
 
 
 class DeviceBatch:
@@ -605,6 +605,47 @@ def run_b200(args):
     else:
         r_inf_north = None
 
+    # ---- BASELINE configs[4]: the same round trip when ONE rank owns the whole batch (NCCL data plane) ----
+    single_origin = None
+    if world > 1 and not args.no_origin and args.workload == "roundtrip":
+        import torch
+        for b in (d_in, d_comp, d_out):
+            b.free()
+        for p_ in (d_csz, d_aout, d_res):
+            l.libdeflate_b200_device_free(ctx.h, p_)
+        dev = torch.device("cuda", local)
+        n_total = n * world
+        rt = shard.OriginRoundTrip(ctx, dist, dev, n_total, chunk, fmt, LEVEL, stages=8)
+        root_in = None
+        if rank == 0:
+            root_in = torch.empty(n_total * chunk, dtype=torch.uint8, device=dev)
+            for r in range(world):        # the batch of the pre-sharded run, rank by rank, through the one pinned buffer
+                synth.synth_fill(pin_in, chunk, r * n, n, 0, threads)
+                ctx._check(l.libdeflate_b200_memcpy_h2d(ctx.h, root_in.data_ptr() + r * n * chunk, pin_in, n * chunk), "h2d")
+                ctx.sync()
+        so_steps = max(1, min(args.steps, 2))
+        info = rt.step(root_in)           # warm-up (NCCL channels, scratch)
+        barrier()
+        ctx.sync()
+        l.libdeflate_b200_timer_start(ctx.h)
+        for _ in range(so_steps):
+            info = rt.step(root_in)
+        ms_so = l.libdeflate_b200_timer_stop_ms(ctx.h)
+        barrier()
+        ms_so = allmax(ms_so)
+        ok = bool((rt.res[:rt.n] == 0).all().item())
+        if rank == 0:
+            ok = ok and bool(torch.equal(rt.out_all, root_in))
+        ok_all = allsum(1.0 if ok else 0.0)
+        single_origin = {"config": "configs[4]: %d x %d B gzip level %d round trip, the whole batch on rank 0, %d GPUs" % (n_total, chunk, LEVEL, world),
+                         "value": round(n_total * chunk * so_steps / 1e6 / (ms_so / 1e3), 2), "unit": "MB/s", "steps": so_steps, "warmup": 1,
+                         "ms_per_step": round(ms_so / so_steps, 3),
+                         "parallelism": "NCCL scatter/gather: grouped ncclSend/ncclRecv of sub-batches root<->ranks overlapped with the kernels, device-side packing, all_gather of byte totals",
+                         "comm_nranks_ok": int(ok_all) == world, "verified": "all ranks SUCCESS; gathered output == input on the root (torch.equal)",
+                         "root_nvlink_bytes_per_step": info["nvlink_bytes"], "compressed_bytes_per_step": info["compressed_bytes_total"],
+                         "timing": "CUDA events on each rank's stream around the steps, max over ranks"}
+        assert int(ok_all) == world, "single-origin round trip failed verification"
+
     line = {
         "metric": metric_name(args), "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
         "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms_max / steps, 4),
@@ -614,7 +655,7 @@ def run_b200(args):
         "kernel_ms_per_step": {k: round(v[0] / steps, 4) for k, v in ktime.items() if v[1]},
         "ratio": round(ratio, 4), "ratio_reference_L6": ref_ratio,
         "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-        "extra": extra,
+        "extra": extra, "single_origin": single_origin,
         "verified": "all %d chunks: verdict SUCCESS, size, device CRC-32(out)==CRC-32(in); %d chunks byte-compared + zlib CRC" % (n, min(256, len(samp))),
     }
     if rank == 0:
@@ -624,7 +665,9 @@ def run_b200(args):
 
 
 def run_e2e(args, ctx, l, ldb, pin_in, n, chunk, fmt, cstride, barrier, allmax, d_comp_ref, csz_ref):
-    """Same metric through the host-buffer C-ABI calls; pinned host memory on both sides."""
+    """Same metric through the host-buffer C-ABI calls a chunk-loop caller would make; pinned host memory on
+    both sides.  The compressed side uses the PACKED forms (one buffer + offset table): the device packs the
+    bound-sized slots, so only produced bytes cross PCIe."""
     import numpy as np
     try:
         import psutil
@@ -634,34 +677,41 @@ def run_e2e(args, ctx, l, ldb, pin_in, n, chunk, fmt, cstride, barrier, allmax, 
     ne = n
     while ne > 1024 and ne * (chunk + cstride + chunk) * 2 > avail // 8:
         ne //= 2
-    pin_comp = l.libdeflate_b200_pinned_malloc(ne * cstride)
+    packed_cap = ne * (cstride + 16)
+    pin_comp = l.libdeflate_b200_pinned_malloc(packed_cap)
     pin_out = l.libdeflate_b200_pinned_malloc(ne * chunk)
     assert pin_comp and pin_out
-    P, S = ctypes.c_void_p, ctypes.c_size_t
+
     def arr(base, stride, cnt):
-        a = (base + np.arange(cnt, dtype=np.uint64) * np.uint64(stride)).astype(np.uint64)
-        return a
+        return (base + np.arange(cnt, dtype=np.uint64) * np.uint64(stride)).astype(np.uint64)
     in_ptrs = arr(pin_in, chunk, ne)
     in_sizes = np.full(ne, chunk, dtype=np.uint64)
-    comp_ptrs = arr(pin_comp, cstride, ne)
-    comp_avail = np.full(ne, cstride, dtype=np.uint64)
     out_ptrs = arr(pin_out, chunk, ne)
     out_avail = np.full(ne, chunk, dtype=np.uint64)
     comp_sizes = np.zeros(ne, dtype=np.uint64)
+    comp_offs = np.zeros(ne + 1, dtype=np.uint64)
     aout = np.zeros(ne, dtype=np.uint64)
     res = np.zeros(ne, dtype=np.int32)
     if args.workload == "decompress":
-        # host copy of the reference streams
-        ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, pin_comp, d_comp_ref.slab, ne * cstride), "d2h")
+        # host copy of the reference streams, packed (16-byte aligned starts) -- outside the timed region
+        tmp = l.libdeflate_b200_pinned_malloc(ne * cstride)
+        ctx._check(l.libdeflate_b200_memcpy_d2h(ctx.h, tmp, d_comp_ref.slab, ne * cstride), "d2h")
         ctx.sync()
         comp_sizes[:] = csz_ref[:ne]
+        comp_offs[1:] = np.cumsum((comp_sizes + np.uint64(15)) & ~np.uint64(15))
+        src = np.ctypeslib.as_array(ctypes.cast(tmp, ctypes.POINTER(ctypes.c_uint8)), shape=(ne * cstride,))
+        dst = np.ctypeslib.as_array(ctypes.cast(pin_comp, ctypes.POINTER(ctypes.c_uint8)), shape=(packed_cap,))
+        for i in range(ne):
+            o, z = int(comp_offs[i]), int(comp_sizes[i])
+            dst[o:o + z] = src[i * cstride:i * cstride + z]
+        l.libdeflate_b200_pinned_free(tmp)
 
     def e2e_step():
         if args.workload == "roundtrip":
-            ctx._check(l.libdeflate_b200_compress_batch_host(ctx.h, fmt, LEVEL, in_ptrs.ctypes.data, in_sizes.ctypes.data,
-                                                             comp_ptrs.ctypes.data, comp_avail.ctypes.data, comp_sizes.ctypes.data, ne), "compress_batch_host")
-        ctx._check(l.libdeflate_b200_decompress_batch_host(ctx.h, fmt, 0, comp_ptrs.ctypes.data, comp_sizes.ctypes.data,
-                                                           out_ptrs.ctypes.data, out_avail.ctypes.data, None, aout.ctypes.data, res.ctypes.data, ne), "decompress_batch_host")
+            ctx._check(l.libdeflate_b200_compress_batch_host_packed(ctx.h, fmt, LEVEL, in_ptrs.ctypes.data, in_sizes.ctypes.data, ne,
+                                                                    pin_comp, packed_cap, comp_offs.ctypes.data, comp_sizes.ctypes.data), "compress_batch_host_packed")
+        ctx._check(l.libdeflate_b200_decompress_batch_host_packed(ctx.h, fmt, 0, pin_comp, comp_offs.ctypes.data, comp_sizes.ctypes.data, ne,
+                                                                  out_ptrs.ctypes.data, out_avail.ctypes.data, None, aout.ctypes.data, res.ctypes.data), "decompress_batch_host_packed")
     for _ in range(min(args.warmup, 2)):
         e2e_step()
     barrier()
@@ -678,19 +728,21 @@ def run_e2e(args, ctx, l, ldb, pin_in, n, chunk, fmt, cstride, barrier, allmax, 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     val = world * ne * chunk * ksteps / 1e6 / dt
     comp_total = int(comp_sizes.sum())
-    # the streams sit in compress_bound()-sized slots: the library moves the whole span with one DMA per
-    # sub-batch, so the slot gaps travel too (both directions) -- counted here as copied bytes
-    span = (ne - 1) * cstride + int(comp_sizes[ne - 1])
+    packed_total = int(comp_offs[ne])
+    small = 16 * ne + 8 * (ne + 1)      # size / offset tables
     if args.workload == "roundtrip":
-        h2d = ne * chunk + span
-        d2h = ne * cstride + ne * chunk      # whole compressed span + outputs are copied back
+        h2d = ne * chunk + packed_total + small
+        d2h = packed_total + ne * chunk + small
     else:
-        h2d = span
-        d2h = ne * chunk
+        h2d = packed_total + small
+        d2h = ne * chunk + small
     l.libdeflate_b200_pinned_free(pin_comp)
     l.libdeflate_b200_pinned_free(pin_out)
     return {"value": round(val, 2), "unit": "MB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "payload_compressed_bytes": comp_total, "chunks_per_gpu": ne, "steps": ksteps, "timing": "host wall clock around synchronous *_batch_host calls, max over ranks"}
+            "payload_compressed_bytes": comp_total, "packed_compressed_bytes": packed_total, "chunks_per_gpu": ne, "steps": ksteps,
+            "api": "libdeflate_b200_compress_batch_host_packed + libdeflate_b200_decompress_batch_host_packed" if args.workload == "roundtrip"
+                   else "libdeflate_b200_decompress_batch_host_packed",
+            "timing": "host wall clock around the synchronous host calls, max over ranks"}
 
 
 def main():
@@ -708,6 +760,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short legs of the other BASELINE configs (decompress-only, checksums, level 12)")
     ap.add_argument("--no-l12", action="store_true", help="skip the level-12 4096 x 1 MiB leg")
+    ap.add_argument("--no-origin", action="store_true", help="N > 1: skip the single-origin (NCCL scatter/gather) leg")
     args = ap.parse_args()
     LEVEL = args.level
     if args.warmup < 3:

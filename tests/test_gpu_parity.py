@@ -178,3 +178,57 @@ def test_reference_test_programs_against_our_library():
             continue        # opt-in perf test in the reference as well (INCLUDE_PERF_TESTS)
         r = subprocess.run([p], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
         assert r.returncode == 0, (p, r.stdout.decode()[-2000:])
+
+
+def _nccl_origin_worker(rank, world, port, n_total, chunk, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import libdeflate_b200 as ldb
+    from libdeflate_b200 import shard
+    import bench
+    ctx = ldb.Context(rank)
+    dev = torch.device("cuda", rank)
+    rt = shard.OriginRoundTrip(ctx, dist, dev, n_total, chunk, ldb.GZIP, 6, stages=4)
+    root_in = None
+    if rank == 0:
+        synth = bench.load_synth()
+        buf = (ctypes.c_uint8 * (n_total * chunk))()
+        synth.synth_fill(buf, chunk, 0, n_total, 0, 4)
+        root_in = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).to(dev)
+    for _ in range(2):
+        info = rt.step(root_in)
+    ok = bool((rt.res[:rt.n] == 0).all().item())
+    if rank == 0:
+        raw = bytes(root_in.cpu().numpy())
+        ok = ok and bytes(rt.out_all.cpu().numpy()) == raw
+        offs, sizes, comp = rt.comp_offsets.tolist(), rt.comp_sizes.tolist(), bytes(rt.comp_all.cpu().numpy())
+        for i in range(0, n_total, 97):
+            ok = ok and zlib.decompress(comp[offs[i]:offs[i] + sizes[i]], 31) == raw[i * chunk:(i + 1) * chunk]
+        q.put((ok, info))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_single_origin_round_trip_over_nccl():
+    """A real sharded batch through the NCCL scatter/gather data plane (needs two GPUs in the box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run through gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, n_total, chunk = 2, 4099, 65536
+    mctx = mp.get_context("spawn")
+    q = mctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [mctx.Process(target=_nccl_origin_worker, args=(r, world, port, n_total, chunk, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, info = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
+    assert info["nvlink_bytes"]["root_out"] == (n_total - n_total // 2) * chunk

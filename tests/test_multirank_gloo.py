@@ -76,3 +76,57 @@ def test_shard_helpers():
         covered += [lo, hi]
     assert covered[0] == 0 and covered[-1] == 524288 + 5
     assert all(covered[2 * i + 1] == covered[2 * i + 2] for i in range(7))
+
+
+def _origin_worker(rank, world, port, n_total, chunk, out):
+    """Single-origin round trip (libdeflate_b200.shard.OriginRoundTrip) over gloo with host tensors: the
+    kernels are the emulator build of the SAME sources (tests only), the data plane code is the product's."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import zlib
+    import libdeflate_b200 as ldb
+    from libdeflate_b200 import build, shard
+    import bench
+    lib = ldb.load_library(build.build_emu())
+    ctx = ldb.Context(0, lib)
+    rt = shard.OriginRoundTrip(ctx, dist, "cpu", n_total, chunk, ldb.GZIP, 6, stages=3)
+    root_in = None
+    if rank == 0:
+        synth = bench.load_synth()
+        buf = (ctypes.c_uint8 * (n_total * chunk))()
+        synth.synth_fill(buf, chunk, 0, n_total, 6, 2)
+        root_in = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8)
+    info = rt.step(root_in)
+    ok_local = bool((rt.res[:rt.n] == 0).all()) and bool((rt.aout[:rt.n] == chunk).all())
+    flags = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(flags, torch.tensor([1 if ok_local else 0], dtype=torch.int64))
+    if rank == 0:
+        raw = bytes(root_in.numpy())
+        same = bytes(rt.out_all.numpy()) == raw
+        # every gathered compressed chunk is a gzip member of its input chunk, found through the offset table
+        offs, sizes, comp = rt.comp_offsets.tolist(), rt.comp_sizes.tolist(), bytes(rt.comp_all.numpy())
+        members_ok = all(zlib.decompress(comp[offs[i]:offs[i] + sizes[i]], 31) == raw[i * chunk:(i + 1) * chunk] for i in range(n_total))
+        out.put((same, members_ok, [int(f.item()) for f in flags], info, offs[-1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_single_origin_round_trip():
+    world, n_total, chunk = 2, 37, 8192       # odd count: the shards differ in size
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_origin_worker, args=(r, world, port, n_total, chunk, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    same, members_ok, flags, info, packed_total = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert same and members_ok and flags == [1, 1]
+    assert info["compressed_bytes_total"] == packed_total
+    # what crossed the "link": the other rank's input out, its compressed bytes + size table and its output in
+    n1 = n_total - (n_total // 2)
+    assert info["nvlink_bytes"]["root_out"] == n1 * chunk
+    assert info["nvlink_bytes"]["root_in"] > n1 * chunk
