@@ -153,6 +153,59 @@ def check_inputs_with_unmapped_gaps(ctx):
         libc.mprotect(base + 3 * page, 2 * page, 3)
 
 
+def gzip_member(plain, flg, level=6, extra=b"EXTRA-field", name=b"file name.txt", comment=b"a comment"):
+    """A gzip member with the optional header fields selected by FLG (RFC 1952 2.3: FTEXT 1, FHCRC 2, FEXTRA 4,
+    FNAME 8, FCOMMENT 16), built by hand around a zlib-made raw stream."""
+    import struct
+    hdr = bytes([0x1f, 0x8b, 8, flg, 0, 0, 0, 0, 0, 255])
+    if flg & 4:
+        hdr += struct.pack("<H", len(extra)) + extra
+    if flg & 8:
+        hdr += name + b"\0"
+    if flg & 16:
+        hdr += comment + b"\0"
+    if flg & 2:
+        hdr += struct.pack("<H", zlib.crc32(hdr) & 0xffff)
+    body = corpus.zlib_raw(plain, level, zlib.Z_DEFAULT_STRATEGY, -15)
+    return hdr + body + struct.pack("<II", zlib.crc32(plain), len(plain) & 0xffffffff), len(hdr)
+
+
+def check_gzip_optional_fields(ctx, orc, ref=None):
+    """ref: lib/gzip_decompress.c:66-98 -- FEXTRA / FNAME / FCOMMENT / FHCRC (and FTEXT) in every combination are
+    skipped with bounds checks; reserved FLG bits, truncation inside any field, a missing NUL and a header that leaves
+    fewer than 8 bytes for the trailer are BAD_DATA.  Verdicts, actual_in and bytes must equal the oracle's (and the
+    unmodified reference's, when it is built)."""
+    plain = corpus.text(3000, 7)
+    cases = []
+    for flg in range(32):
+        z, hlen = gzip_member(plain, flg)
+        cases.append(z)
+        cases.append(z + b"trailing garbage")                      # actual_in stops at the member's end
+        for cut in sorted(set([10, 11, 12, hlen - 1, hlen, hlen + 1, len(z) - 9, len(z) - 8, len(z) - 1])):
+            if 0 < cut < len(z):
+                cases.append(z[:cut])
+    for bad in (0x20, 0x40, 0x80, 0xE0):
+        cases.append(gzip_member(plain, 0)[0][:3] + bytes([bad]) + gzip_member(plain, 0)[0][4:])
+    z, _ = gzip_member(plain, 8, name=b"x" * 40)
+    cases.append(z[:10] + z[10:].replace(b"\0", b"\1", 1))          # FNAME never terminated before the data runs out?
+    cases.append(gzip_member(b"", 4 | 8 | 16 | 2)[0])                # empty payload behind a full header
+    z, _ = gzip_member(plain, 4, extra=b"")                          # XLEN = 0
+    cases.append(z)
+    z, _ = gzip_member(plain, 4, extra=b"q" * 300)
+    cases.append(z)
+    cases.append(z[:12 + 100])                                      # cut inside FEXTRA
+    got = ctx.decompress_batch_host(cases, [len(plain)] * len(cases), 2)
+    seen = set()
+    for z, g in zip(cases, got):
+        o = orc.decompress(z, len(plain), 2)
+        assert g[0] == o[0] and (o[0] != 0 or g == o), ("gzip header case", z[:24].hex(), g[0], o[0], g[2:], o[2:])
+        if ref is not None:
+            r = ref.decompress(z, len(plain), 2)
+            assert r[0] == o[0] and (o[0] != 0 or r == o), ("oracle vs reference", z[:24].hex(), r[0], o[0])
+        seen.add(o[0])
+    assert seen >= {0, 1}, seen
+
+
 def fuzz_cases(n_cases, seed, max_size=20000):
     rng = random.Random(seed)
     base = []

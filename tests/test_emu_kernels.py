@@ -20,6 +20,10 @@ def test_inflate_valid_streams_emulated(emu_ctx, oracle, reflib):
     pc.check_decompress_valid(emu_ctx, oracle, streams)
 
 
+def test_gzip_optional_header_fields_emulated(emu_ctx, oracle, reflib):
+    pc.check_gzip_optional_fields(emu_ctx, oracle, reflib)
+
+
 def test_inflate_large_chunks_emulated(emu_ctx):
     pc.check_decompress_large(emu_ctx, sizes=(150000,), levels=(0, 6))
 

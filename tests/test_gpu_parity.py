@@ -74,6 +74,75 @@ def test_host_inputs_with_unmapped_gaps(gpu_ctx):
     pc.check_inputs_with_unmapped_gaps(gpu_ctx)
 
 
+def test_gzip_optional_header_fields(gpu_ctx, oracle):
+    pc.check_gzip_optional_fields(gpu_ctx, oracle)
+
+
+def test_compress_1mib_chunks_levels_10_12(gpu_ctx, oracle):
+    """BASELINE configs[3] shape: 1 MiB chunks through the near-optimal levels (the ring is crossed 16 times, the
+    DP segment logic 512 times per chunk): round trip, bound, and the ratio next to the reference's."""
+    chunks = [corpus.text(1 << 20, 11), corpus.mixed(1 << 20, 12), corpus.rand(1 << 20, 13), corpus.zeros(1 << 20)]
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libdeflate_ref.so")
+    ref = None
+    if os.path.exists(ref_so):
+        import libdeflate_b200 as ldb
+        from conftest import _load_ref
+        ref = ldb.Api(_load_ref(ref_so))
+    for lvl in (10, 12):
+        zs = gpu_ctx.compress_batch_host(chunks, lvl, 0)
+        for c, z in zip(chunks, zs):
+            assert z is not None and len(z) <= oracle.l.oracle_compress_bound(0, len(c))
+            assert zlib.decompress(z, -15) == c
+            r = oracle.decompress(z, len(c), 0)
+            assert r[0] == 0 and r[1] == c and r[2] == len(z)
+            if ref is not None:
+                assert len(z) <= 1.05 * len(ref.compress(c, lvl, 0)) + 64, ("ratio vs reference", lvl, len(z), len(ref.compress(c, lvl, 0)))
+
+
+def test_two_contexts_two_host_threads(gpu_ctx):
+    """Distinct objects may be used concurrently from different threads (ref: libdeflate.h:56-57, 178-179): two
+    contexts, two threads, plus the classic single-buffer API from both at once."""
+    import threading
+    import libdeflate_b200 as ldb
+    errs = []
+
+    def work(seed):
+        try:
+            ctx = ldb.Context(0)
+            api = ldb.Api()
+            chunks = [corpus.text(30000 + 17 * i, seed * 100 + i) for i in range(40)]
+            for _ in range(3):
+                zs = ctx.compress_batch_host(chunks, 6, 2)
+                got = ctx.decompress_batch_host(zs, [len(c) for c in chunks], 2)
+                assert all(g[0] == 0 and g[1] == c for g, c in zip(got, chunks))
+                z = api.compress(chunks[0], 6, 1)
+                assert api.decompress(z, len(chunks[0]), 1)[1] == chunks[0]
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+    ts = [threading.Thread(target=work, args=(s,)) for s in (1, 2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+
+
+def test_two_devices_one_process():
+    """Kernel attributes are per device: a second context on another GPU of the same process must work."""
+    import libdeflate_b200 as ldb
+    if ldb.lib().libdeflate_b200_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run through gpurun --gpus 2)")
+    chunks = [corpus.text(65536, i) for i in range(64)]
+    outs = []
+    for dev in (0, 1, 0):
+        ctx = ldb.Context(dev)
+        zs = ctx.compress_batch_host(chunks, 6, 2)
+        got = ctx.decompress_batch_host(zs, [len(c) for c in chunks], 2)
+        assert all(g[0] == 0 and g[1] == c for g, c in zip(got, chunks))
+        outs.append(zs)
+    assert outs[0] == outs[1] == outs[2]
+
+
 def test_decompress_large_chunks(gpu_ctx):
     pc.check_decompress_large(gpu_ctx)
 
