@@ -132,6 +132,7 @@ struct libdeflate_b200_ctx {
 	ldb_buf d_pack;			// device: packed output of the *_packed host calls
 	ldb_buf d_params;		// device: pointer/size arrays for host-buffer calls
 	ldb_buf h_pinned;		// pinned host staging
+	ldb_buf h_pinned_tab;		// pinned host: size / offset tables read back while kernels keep running
 	u64 launches;
 	cudaEvent_t ev_start, ev_stop;
 	cudaStream_t stream_h2d, stream_d2h;	// copy streams of the pipelined host-buffer path
@@ -253,6 +254,7 @@ extern "C" void libdeflate_b200_ctx_destroy(struct libdeflate_b200_ctx *ctx)
 	cudaFree(ctx->d_pack.p);
 	cudaFree(ctx->d_params.p);
 	if (ctx->h_pinned.p) cudaFreeHost(ctx->h_pinned.p);
+	if (ctx->h_pinned_tab.p) cudaFreeHost(ctx->h_pinned_tab.p);
 	delete ctx;
 }
 
@@ -907,8 +909,12 @@ extern "C" int libdeflate_b200_compress_batch_host_packed(struct libdeflate_b200
 	size_t *d_os = (size_t *)(dparam + pb + align_up(n * sizeof(void *), 256));
 	size_t *d_on = (size_t *)(dparam + sz_off);
 	u64 *d_offs = (u64 *)(dparam + off_off);
-	u64 *r_offs = (u64 *)(hparam + off_off);
-	size_t *r_on = (size_t *)(hparam + sz_off);
+	// the tables come back into PINNED memory: a device-to-host copy into pageable memory would block
+	// the host until the stream gets there, i.e. serialise the sub-batches
+	rc = ldb_reserve_pinned(ctx->h_pinned_tab, par_bytes - sz_off);
+	if (rc) return rc;
+	size_t *r_on = (size_t *)ctx->h_pinned_tab.p;
+	u64 *r_offs = (u64 *)((u8 *)ctx->h_pinned_tab.p + (off_off - sz_off));
 
 	const size_t S = pipelined ? pipe_stages(n, in_sb.slab_bytes + slots / 3, 1024) : 1;
 	pipe_events ev;
