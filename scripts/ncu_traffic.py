@@ -1,5 +1,5 @@
 """Parses `ncu --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum` output of a
-bench.py run and records DRAM bytes per launch of the two hot kernels in profiles/dram_traffic.json, keyed by
+bench.py run and records DRAM bytes per launch of the hot kernels in profiles/dram_traffic.json, keyed by
 the bench configuration.  bench.py fills roofline.traffic from that file when the configuration matches."""
 import csv
 import json
@@ -20,7 +20,7 @@ def main():
         if r is hdr or len(r) <= iv or r[ik] == "Kernel Name":
             continue
         name = r[ik].split("(")[0]
-        if not name.startswith(("ldb_inflate_kernel", "ldb_deflate_lz_kernel")):
+        if not name.startswith(("ldb_inflate_decode_kernel", "ldb_inflate_resolve_kernel", "ldb_deflate_lz_kernel")):
             continue
         val = float(r[iv].replace(",", ""))
         unit = r[iu].lower()
