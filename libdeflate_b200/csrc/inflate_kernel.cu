@@ -195,6 +195,21 @@ __device__ __forceinline__ u32 inf_peek(inf_lane &s)
 	return __funnelshift_r(s.w0, s.w1, s.bitpos);
 }
 
+// the same refill for the hot loop, written with selects: the window registers are updated in place,
+// which keeps the compiler from shuttling them between copies at every merge point
+__device__ __forceinline__ u32 inf_peek_hot(inf_lane &s)
+{
+	const bool rf = s.bitpos >= 32;
+	u32 nw = s.w2;
+	if (rf) nw = inf_ld_word(s, s.wpos + 12);
+	s.w0 = rf ? s.w1 : s.w0;
+	s.w1 = rf ? s.w2 : s.w1;
+	s.w2 = nw;
+	s.wpos += rf ? 4u : 0u;
+	s.bitpos -= rf ? 32u : 0u;
+	return __funnelshift_r(s.w0, s.w1, s.bitpos);
+}
+
 __device__ __forceinline__ u32 inf_take(inf_lane &s, u32 nbits)
 {
 	u32 v = inf_peek(s) & ((1u << nbits) - 1);
@@ -619,71 +634,97 @@ __device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
 // happens once per service phase, outside this loop.
 __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
 {
-	// (written without early returns: one merge point keeps the loop-carried registers in place)
+	// Written as ONE predicated block (selects instead of branches, stores under a predicate, no early
+	// returns): with ~31 of 32 lanes active every path is taken by somebody in every step anyway, so
+	// branches only add reconvergence bookkeeping and register shuttling at the merge points.
+	const bool act = s.state >= ST_LIT;
 	const bool isoff = s.state == ST_OFF;
-	u32 bits = inf_peek(s);
-	bool dead = false;
-	if (!isoff && s.wpos + 8 > s.in_nal) {
-		// start of a litlen symbol with virtual zero bytes (nearly) in play: P >= 8n+9 means the
-		// reference's refill over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
-		dead = inf_bits_past_end(s) >= 9;
+	// refill (bitpos < 32 afterwards)
+	const bool rf = act && s.bitpos >= 32;
+	u32 nw = s.w2;
+	if (rf) nw = inf_ld_word(s, s.wpos + 12);
+	s.w0 = rf ? s.w1 : s.w0;
+	s.w1 = rf ? s.w2 : s.w1;
+	s.w2 = nw;
+	s.wpos += rf ? 4u : 0u;
+	s.bitpos -= rf ? 32u : 0u;
+	u32 bits = __funnelshift_r(s.w0, s.w1, s.bitpos);
+	// start of a litlen symbol with virtual zero bytes (nearly) in play: P >= 8n+9 means the reference's
+	// refill over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
+	const bool dead = act && !isoff && s.wpos + 8 > s.in_nal && inf_bits_past_end(s) >= 9;
+	const bool live = act && !dead;
+	// table lookup; litlen and offset tables share the entry encoding
+	const u16 *tab = (const u16 *)(sm + (isoff ? INF_SM_OTAB : INF_SM_LTAB)) + lane;
+	const u32 mainbits = isoff ? INF_OB : INF_LB;
+	u32 e = tab[(bits & ((1u << mainbits) - 1)) * 32];
+	u32 adv = 0;
+	if (live && e >= LE_SUB_FLAG) {
+		const u32 sstart = ((e >> 4) & 0x3ff) << 1;
+		const u32 sb = e & 15;
+		bits >>= mainbits;
+		adv = mainbits;
+		const u32 idx = sstart + (bits & ((1u << sb) - 1));
+		const u32 sub_sm = isoff ? INF_OSUB_SM : INF_LSUB_SM;
+		e = idx < sub_sm ? tab[((1u << mainbits) + idx) * 32] : ovf[(isoff ? INF_OVF_L : 0) + idx - sub_sm];
 	}
-	if (dead) {
-		s.verdict = LDB_BAD_DATA;
-		s.state = ST_DONE;
-	} else {
-		const u16 *tab = (const u16 *)(sm + (isoff ? INF_SM_OTAB : INF_SM_LTAB)) + lane;
-		const u32 mainbits = isoff ? INF_OB : INF_LB;
-		u32 e = tab[(bits & ((1u << mainbits) - 1)) * 32];
-		if (e >= LE_SUB_FLAG) {
-			const u32 sstart = ((e >> 4) & 0x3ff) << 1;
-			const u32 sb = e & 15;
-			bits >>= mainbits;
-			s.bitpos += mainbits;
-			const u32 idx = sstart + (bits & ((1u << sb) - 1));
-			const u32 sub_sm = isoff ? INF_OSUB_SM : INF_LSUB_SM;
-			e = idx < sub_sm ? tab[((1u << mainbits) + idx) * 32] : ovf[(isoff ? INF_OVF_L : 0) + idx - sub_sm];
-		}
-		const u32 cl = e & 15;
-		s.bitpos += cl;
-		if (e < LE_LEN_FLAG) {
-			// literal (only litlen tables hold them)
-			if (s.n_lit == s.lit_limit) {
-				s.verdict = LDB_INSUFFICIENT_SPACE;
-				s.state = ST_DONE;
-			} else {
-				inf_put_byte(s, e >> 4);
-			}
-		} else if (e & LE_EOB_FLAG) {
-			s.verdict = LDB_SUCCESS;
-			s.state = s.is_final ? ST_DONE : ST_HEADER;
-		} else {
-			// length or offset: base(slot) + extra bits
-			bits >>= cl;
-			const u32 slot = (e >> 4) & 31;
-			const u32 k = isoff ? 1 : 2;			// slots per doubling = 1 << k
-			const u32 first = 2u << k;			// first slot with extra bits: 4 (offsets), 8 (lengths)
-			const u32 origin = isoff ? 1 : 3;
-			u32 eb = slot >= first ? (slot - (1u << k)) >> k : 0;
-			u32 val = slot >= first ? origin + (((1u << k) + (slot & ((1u << k) - 1))) << eb) : origin + slot;
-			if (!isoff && slot >= 28) { val = 258; eb = 0; }	// the one irregular entry: length 258, no extra bits
-			val += bits & ((1u << eb) - 1);
-			s.bitpos += eb;
-			if (!isoff) {
-				// length: "no room" is decided before the offset is looked at (decompress_template.h:696-701)
-				const bool fits = val <= s.lit_limit - s.n_lit;
-				s.verdict = LDB_INSUFFICIENT_SPACE;	// only read in ST_DONE
-				s.pend_len = val;
-				s.state = fits ? ST_OFF : ST_DONE;
-			} else if (val > inf_out_pos(s)) {
-				s.verdict = LDB_BAD_DATA;
-				s.state = ST_DONE;
-			} else {
-				inf_put_match(s, s.pend_len, val);
-				s.state = ST_LIT;
-			}
-		}
+	const u32 cl = e & 15;
+	adv += cl;
+	const bool is_lit = live && e < LE_LEN_FLAG;
+	const bool is_eob = live && !is_lit && (e & LE_EOB_FLAG) != 0;
+	const bool is_val = live && !is_lit && !is_eob;
+	// literal: enters the accumulator from the top, every fourth one completes a word
+	const bool lit_full = is_lit && s.n_lit == s.lit_limit;
+	const bool put = is_lit && !lit_full;
+	const u32 acc2 = __funnelshift_r(s.acc, e >> 4, 8);
+	s.acc = put ? acc2 : s.acc;
+	s.n_lit += put ? 1u : 0u;
+	if (put && (s.n_lit & 3) == 0) *(u32 *)(s.lit + s.n_lit - 4) = s.acc;
+	// length or offset: base(slot) + extra bits, the same arithmetic up to k
+	const u32 vbits = bits >> cl;
+	const u32 slot = (e >> 4) & 31;
+	const u32 k = isoff ? 1 : 2;			// slots per doubling = 1 << k
+	const u32 first = 2u << k;			// first slot with extra bits: 4 (offsets), 8 (lengths)
+	const u32 origin = isoff ? 1 : 3;
+	u32 eb = slot >= first ? (slot - (1u << k)) >> k : 0;
+	u32 val = slot >= first ? origin + (((1u << k) + (slot & ((1u << k) - 1))) << eb) : origin + slot;
+	const bool len258 = !isoff && slot >= 28;	// the one irregular entry: length 258, no extra bits
+	val = len258 ? 258u : val;
+	eb = len258 ? 0u : eb;
+	val += vbits & ((1u << eb) - 1);
+	adv += is_val ? eb : 0u;
+	s.bitpos += live ? adv : 0u;
+	const bool is_len = is_val && !isoff;
+	const bool is_offv = is_val && isoff;
+	// length: "no room" is decided before the offset is looked at (decompress_template.h:696-701)
+	const bool len_fits = val <= s.lit_limit - s.n_lit;
+	const bool off_ok = val <= inf_out_pos(s);
+	const bool emit = is_offv && off_ok;
+	// the match record (and, before it, a literal-run record when more than 255 literals are pending)
+	const u32 litrun = s.n_lit - s.lit_mark;
+	const bool big = litrun > 255;
+	if (emit) {
+		u32 *r = s.rec_end - s.n_rec - 1;
+		if (big) { *r = LDB_TOK_PURE_FLAG | litrun; r--; }
+		*r = ((big ? 0u : litrun) << 23) | ((s.pend_len - 3) << 15) | (val - 1);
 	}
+	s.n_rec += emit ? (big ? 2u : 1u) : 0u;
+	s.lit_mark = emit ? s.n_lit : s.lit_mark;
+	s.lit_limit -= emit ? s.pend_len : 0u;
+	s.pend_len = is_len ? val : s.pend_len;
+	// next state / verdict (the verdict is only read in ST_DONE)
+	u32 st = s.state, vd = s.verdict;
+	st = is_offv ? (off_ok ? (u32)ST_LIT : (u32)ST_DONE) : st;
+	vd = is_offv ? (u32)LDB_BAD_DATA : vd;
+	st = is_len ? (len_fits ? (u32)ST_OFF : (u32)ST_DONE) : st;
+	vd = is_len ? (u32)LDB_INSUFFICIENT_SPACE : vd;
+	st = is_eob ? (s.is_final ? (u32)ST_DONE : (u32)ST_HEADER) : st;
+	vd = is_eob ? (u32)LDB_SUCCESS : vd;
+	st = lit_full ? (u32)ST_DONE : st;
+	vd = lit_full ? (u32)LDB_INSUFFICIENT_SPACE : vd;
+	st = dead ? (u32)ST_DONE : st;
+	vd = dead ? (u32)LDB_BAD_DATA : vd;
+	s.state = st;
+	s.verdict = vd;
 }
 
 // ---- the decode kernel --------------------------------------------------------------
@@ -871,7 +912,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 		// ---- decode phase: INF_QUANTUM steps, one symbol per lane and step ---------------------
 #pragma unroll 1
 		for (int it = 0; it < INF_QUANTUM; it++) {
-			if (s.state >= ST_LIT) inf_decode_step(s, sm, ovf, lane);
+			inf_decode_step(s, sm, ovf, lane);
 			if ((it & 31) == 31 && !__any_sync(LDB_FULL_MASK, s.state >= ST_LIT)) break;
 		}
 		__syncwarp();
