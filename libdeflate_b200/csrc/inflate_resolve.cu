@@ -34,7 +34,9 @@
 #define RES_STG     4096u	// staging ring: the group being assembled, position q at q % 4096
 #define RES_SMASK   (RES_STG - 1)
 #define RES_SPAN    2048u	// most output bytes one group of records may cover
+#ifndef RES_LIT_FAST
 #define RES_LIT_FAST 16u	// literal runs up to this are placed by the owning lane in one step
+#endif
 #define RES_SM_BYTES RES_STG
 #ifndef RES_PER_SM
 #define RES_PER_SM  32		// warps (= chunks) per SM; measured 8 / 16 / 24 / 32: 25.9 / 14.2 / 10.6 / 9.0 ms per 4 GiB
@@ -179,7 +181,7 @@ __device__ __forceinline__ void res_copy_coop(const u8 *win, u8 *stg, u32 B, u32
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, RES_PER_SM)
 ldb_inflate_resolve_kernel(ldb_inflate_args a, u32 *work_counter)
 {
 	LDB_DYN_SMEM(sm);

@@ -13,11 +13,11 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    # decode kernel: offset table geometry vs warps per SM (the global overflow-subtable load is the top stall)
-    "o6s16w7": ["-DINF_OB=6", "-DINF_OSUB_SM=16", "-DINF_WPC=7"],      # 480 B/lane, 2 CTAs x 7 warps
-    "o6s32w13": ["-DINF_OB=6", "-DINF_OSUB_SM=32", "-DINF_WPC=13"],    # 512 B/lane, 1 CTA x 13 warps
-    "o5s64w13": ["-DINF_OB=5", "-DINF_OSUB_SM=64", "-DINF_WPC=13"],    # 512 B/lane, 1 CTA x 13 warps
+    # resolve kernel (32 single-warp CTAs per SM is the hardware's CTA limit)
+    "lf8": ["-DRES_LIT_FAST=8u"],
 }
+# decode kernel, offset table geometry: 6-bit main + 16 shared subtable entries at 14 warps per SM 17.5 ms (= default);
+# 13-warp geometries 27-28 ms (65536 chunks no longer fit one wave of lanes)
 # decode steps between service phases, -DINF_QUANTUM=128/384/1024: 17.4 / 17.5 / 17.6 ms
 # resolve kernel, warps (= chunks) per SM, -DRES_PER_SM=8/16/24/32: 25.9 / 14.2 / 10.6 / 9.0 ms per 65536 x 64 KiB
 # measured and dropped: resumable chain walk of the deflate search (-DLZ_QUANTUM=6/8/12): 86.9 / 86.4 / 84.3 ms vs 79.2 ms
