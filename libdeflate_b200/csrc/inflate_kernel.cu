@@ -114,9 +114,7 @@ static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry")
 
 // ST_LIT: the next thing in the stream is a litlen symbol; ST_OFF: a length has been decoded, its
 // offset is next; ST_DONE: the stream has ended with s.verdict (finished in the service phase)
-// ST_LIT_W / ST_OFF_W: the symbol's entry sits in an overflow subtable in global memory; the load has
-// been issued into s.e_pend and the lane sits out one step instead of stalling the warp on it
-enum { ST_IDLE = 0, ST_HEADER = 1, ST_BUILD = 2, ST_STORED = 3, ST_DONE = 4, ST_LIT = 5, ST_OFF = 6, ST_LIT_W = 7, ST_OFF_W = 8 };
+enum { ST_IDLE = 0, ST_HEADER = 1, ST_BUILD = 2, ST_STORED = 3, ST_DONE = 4, ST_LIT = 5, ST_OFF = 6 };
 
 size_t ldb_inflate_overflow_bytes_per_stream(void) { return INF_OVF_ENTRIES * sizeof(u16); }
 
@@ -150,7 +148,6 @@ struct inf_lane {
 	u32 hlit, hdist, is_static;
 	u32 stored_len, stored_src;
 	u32 pend_len;		// decoded match length whose offset has not been decoded yet (ST_OFF)
-	u32 e_pend;		// ST_*_W: the overflow-subtable entry being loaded
 	// bookkeeping
 	u32 chunk;		// chunk index
 	u32 hdr_bytes;		// wrapper header size
@@ -641,8 +638,7 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	// returns): with ~31 of 32 lanes active every path is taken by somebody in every step anyway, so
 	// branches only add reconvergence bookkeeping and register shuttling at the merge points.
 	const bool act = s.state >= ST_LIT;
-	const bool isoff = s.state == ST_OFF || s.state == ST_OFF_W;
-	const bool resumed = s.state >= ST_LIT_W;	// main-table bits already consumed, entry in e_pend
+	const bool isoff = s.state == ST_OFF;
 	// refill (bitpos < 32 afterwards)
 	const bool rf = act && s.bitpos >= 32;
 	u32 nw = s.w2;
@@ -655,33 +651,22 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	u32 bits = __funnelshift_r(s.w0, s.w1, s.bitpos);
 	// start of a litlen symbol with virtual zero bytes (nearly) in play: P >= 8n+9 means the reference's
 	// refill over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
-	const bool dead = act && !resumed && !isoff && s.wpos + 8 > s.in_nal && inf_bits_past_end(s) >= 9;
-	bool live = act && !dead;
+	const bool dead = act && !isoff && s.wpos + 8 > s.in_nal && inf_bits_past_end(s) >= 9;
+	const bool live = act && !dead;
 	// table lookup; litlen and offset tables share the entry encoding
 	const u16 *tab = (const u16 *)(sm + (isoff ? INF_SM_OTAB : INF_SM_LTAB)) + lane;
 	const u32 mainbits = isoff ? INF_OB : INF_LB;
 	u32 e = tab[(bits & ((1u << mainbits) - 1)) * 32];
-	e = resumed ? s.e_pend : e;
 	u32 adv = 0;
-	bool defer = false;
-	if (live && !resumed && e >= LE_SUB_FLAG) {
+	if (live && e >= LE_SUB_FLAG) {
 		const u32 sstart = ((e >> 4) & 0x3ff) << 1;
 		const u32 sb = e & 15;
 		bits >>= mainbits;
 		adv = mainbits;
 		const u32 idx = sstart + (bits & ((1u << sb) - 1));
 		const u32 sub_sm = isoff ? INF_OSUB_SM : INF_LSUB_SM;
-		if (idx < sub_sm) {
-			e = tab[((1u << mainbits) + idx) * 32];
-		} else {
-			// split phase: issue the global load now, use it in the next step -- the other lanes of
-			// the warp go on instead of waiting ~an L2 round trip for this one
-			s.e_pend = ovf[(isoff ? INF_OVF_L : 0) + idx - sub_sm];
-			defer = true;
-		}
+		e = idx < sub_sm ? tab[((1u << mainbits) + idx) * 32] : ovf[(isoff ? INF_OVF_L : 0) + idx - sub_sm];
 	}
-	s.bitpos += defer ? adv : 0u;
-	live = live && !defer;
 	const u32 cl = e & 15;
 	adv += cl;
 	const bool is_lit = live && e < LE_LEN_FLAG;
@@ -728,7 +713,6 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	s.pend_len = is_len ? val : s.pend_len;
 	// next state / verdict (the verdict is only read in ST_DONE)
 	u32 st = s.state, vd = s.verdict;
-	st = put ? (u32)ST_LIT : st;	// (a literal may have been a resumed ST_LIT_W)
 	st = is_offv ? (off_ok ? (u32)ST_LIT : (u32)ST_DONE) : st;
 	vd = is_offv ? (u32)LDB_BAD_DATA : vd;
 	st = is_len ? (len_fits ? (u32)ST_OFF : (u32)ST_DONE) : st;
@@ -739,7 +723,6 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	vd = lit_full ? (u32)LDB_INSUFFICIENT_SPACE : vd;
 	st = dead ? (u32)ST_DONE : st;
 	vd = dead ? (u32)LDB_BAD_DATA : vd;
-	st = defer ? (isoff ? (u32)ST_OFF_W : (u32)ST_LIT_W) : st;
 	s.state = st;
 	s.verdict = vd;
 }
@@ -763,7 +746,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 	s.chunk = 0xffffffffu;
 	s.in = nullptr; s.in_al = nullptr; s.in_a0 = 0; s.in_n = 0; s.in_nal = 0; s.wpos = 0; s.w0 = 0; s.w1 = 0; s.w2 = 0; s.bitpos = 0;
 	s.lit = nullptr; s.rec_end = nullptr; s.n_lit = 0; s.n_rec = 0; s.lit_mark = 0; s.lit_limit = 0; s.out_avail = 0; s.acc = 0;
-	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.pend_len = 0; s.e_pend = 0;
+	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.pend_len = 0;
 	bool exhausted = false;
 
 	// the bookkeeping of a stream that has ended (ST_DONE) with s.verdict; the lane becomes idle
