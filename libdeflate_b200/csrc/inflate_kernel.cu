@@ -99,8 +99,11 @@
 #define INF_WPC        5		// independent warps per CTA
 #endif
 
-static_assert(INF_L_ENTRIES >= 160, "the litlen region doubles as the 320-byte code-length scratch");
-static_assert(INF_O_ENTRIES >= 64, "the offset region doubles as the 128-byte precode table scratch");
+// header-parsing scratch inside the (about to be rebuilt) table slots, two bytes per u16 slot: the 320 code
+// lengths take slots 0..159 of the litlen region and, where that is shorter, run on into the offset region
+// (the two regions are adjacent and interleaved the same way); the 128-byte precode table follows them
+#define INF_SCR_PRETAB_SLOT (INF_L_ENTRIES >= 160 ? INF_L_ENTRIES : 160)	// first slot of the precode table, counted from the litlen region
+static_assert(INF_L_ENTRIES + INF_O_ENTRIES >= INF_SCR_PRETAB_SLOT + 64, "code-length scratch + precode table must fit the two table regions");
 static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry");
 
 // entry encodings (u16)
@@ -328,7 +331,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 	// scratch inside the lane's own (about to be rebuilt) table slots, two bytes per u16 slot:
 	// <= 320 code lengths in the litlen region, the 128-entry precode table in the offset region
 	u8 *lens = sm + INF_SM_LTAB;		// scr_idx(i, lane)
-	u8 *pretab = sm + INF_SM_OTAB;		// scr_idx(i, lane)
+	u8 *pretab = sm + INF_SM_LTAB + INF_SCR_PRETAB_SLOT * 64;	// scr_idx(i, lane); a slot row is 32 lanes x 2 bytes
 	static const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 	s.is_final = inf_take(s, 1);

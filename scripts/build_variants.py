@@ -14,7 +14,9 @@ GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]    
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
     # resolve kernel (32 single-warp CTAs per SM is the hardware's CTA limit)
-    "lf8": ["-DRES_LIT_FAST=8u"],
+    # decode table geometry at the same 448 B per lane (15 warps per SM): 6-bit offset main table, 16 + 16 shared subtable entries
+    "g6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16"],
+    "g6b": ["-DINF_LSUB_SM=0", "-DINF_OB=6", "-DINF_OSUB_SM=32"],
 }
 # decode kernel, offset table geometry: 6-bit main + 16 shared subtable entries at 14 warps per SM 17.5 ms (= default);
 # 13-warp geometries 27-28 ms (65536 chunks no longer fit one wave of lanes)
