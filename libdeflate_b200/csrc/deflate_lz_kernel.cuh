@@ -131,7 +131,10 @@ __device__ __forceinline__ lz_params lz_level_params(int level)
 	case 3: return {8, 32, 0, 0};
 	case 4: return {12, 48, 0, 0};
 	case 5: return {12, 48, 1, 0};
-	case 6: return {24, 96, 1, 0};
+#ifndef LZ_L6_DEPTH
+#define LZ_L6_DEPTH 24
+#endif
+	case 6: return {LZ_L6_DEPTH, 96, 1, 0};
 	case 7: return {48, 160, 1, 0};
 	case 8: return {96, 258, 2, 0};		// lazy2: one more position of lookahead (ref: deflate_compress.c:2742-2776)
 	case 9: return {200, 258, 2, 0};
@@ -1275,7 +1278,10 @@ ldb_deflate_lz_kernel(ldb_deflate_args a)
 				// A run starts its walk without knowing where the parse really enters it, so short
 				// runs cost a little ratio (L6: +0.9 % at 16 vs 32) and buy parallelism; the deep
 				// levels, which are chosen for ratio, keep 32.
-				const u32 run_len = a.level >= 7 ? 32 : 16;
+#ifndef LZ_RUN_SHORT
+#define LZ_RUN_SHORT 16
+#endif
+				const u32 run_len = a.level >= 7 ? 32 : LZ_RUN_SHORT;
 				// runs are handed out dynamically (shared counter): lanes whose runs are cheap
 				// (long matches, few searches) take more of them, which keeps the warp busy
 				u32 i = 0, i_end = 0;

@@ -744,6 +744,9 @@ static int ldb_decompress_batch_host_impl(struct libdeflate_b200_ctx *ctx, int f
 	staged_batch in_sb{}, out_sb{};
 	rc = stage_layout(ctx, ctx->d_stage_in, h_in, h_in_nbytes, n, !pipelined, false, dparam, hparam, &in_sb, in_one_alloc);
 	if (!rc) rc = stage_layout(ctx, ctx->d_stage_out, (const void *const *)h_out, h_out_avail, n, false, true, dparam + pb, hparam + pb, &out_sb);
+	// whole output spans travel back: what the kernels do not write (room past actual_out, failed chunks) must
+	// not be bytes of an earlier call
+	if (!rc) rc = cudaMemsetAsync(out_sb.d_base, 0, out_sb.slab_bytes, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "memset out", __FILE__, __LINE__);
 	if (!rc) rc = cudaMemcpyAsync(dparam, hparam, 2 * pb, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? 0 : ldb_fail(cudaGetLastError(), "H2D params", __FILE__, __LINE__);
 	size_t *d_ain = (size_t *)(dparam + res_off);
 	size_t *d_aout = (size_t *)(dparam + res_off + align_up(n * sizeof(size_t), 256));
@@ -1159,7 +1162,7 @@ extern "C" int libdeflate_b200_bgzf_decompress(struct libdeflate_b200_ctx *ctx, 
 			nblk = k;
 			total_out = opos;
 			if (total_out > out_avail) { *result = LDB_INSUFFICIENT_SPACE; return 0; }
-			if (nblk == 0) { *result = LDB_SUCCESS; return 0; }
+			if (nblk == 0) return 0;	// zero members: not a gzip file (the reference's gunzip refuses an empty file too) -> BAD_DATA
 			continue;
 		}
 		int rc = libdeflate_b200_decompress_batch_host(ctx, LIBDEFLATE_B200_GZIP, LIBDEFLATE_B200_EXACT_OUT_SIZE, ip, isz, op, oav,

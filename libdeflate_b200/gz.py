@@ -20,6 +20,8 @@ def uncompressed_size(data):
         if data[pos:pos + 3] != b"\x1f\x8b\x08" or not data[pos + 3] & 4:
             raise ValueError("not a blocked gzip (BGZF) file")
         xlen = struct.unpack_from("<H", data, pos + 10)[0]
+        if pos + 12 + xlen + 8 > len(data):      # the extra field and a trailer must fit (as the C walker checks)
+            raise ValueError("corrupt BGZF member at byte %d" % pos)
         x, bsize = 0, 0
         while x + 4 <= xlen:
             si1, si2, slen = struct.unpack_from("<BBH", data, pos + 12 + x)
@@ -32,6 +34,8 @@ def uncompressed_size(data):
         pos += bsize
     if pos != len(data):
         raise ValueError("trailing bytes after the last BGZF member")
+    if total > 1032 * len(data) + 64:            # DEFLATE cannot expand more than ~1032:1: a lying ISIZE
+        raise ValueError("BGZF size fields exceed what the file can decode to")
     return total
 
 
@@ -61,6 +65,8 @@ def decompress_members(api, data):
             res, piece, ain, _aout = api.decompress(data[pos:], avail, ldb.GZIP)
             if res != 3:        # LIBDEFLATE_INSUFFICIENT_SPACE
                 break
+            if avail > 1032 * (len(data) - pos) + (1 << 16):
+                break           # more room cannot help: DEFLATE expands at most ~1032:1 (and streams >= 4 GiB are unsupported)
             avail *= 2
         if res != 0:
             raise ValueError("decompression failed: libdeflate_result %d at byte %d" % (res, pos))

@@ -14,6 +14,11 @@ GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]    
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
     # resolve kernel (32 single-warp CTAs per SM is the hardware's CTA limit)
+    # deflate kernel: half the threads per CTA (2 search runs per thread, 128 registers each)
+    "t512": ["-DLZ_THREADS=512"],
+    "run8": ["-DLZ_RUN_SHORT=8"],
+    "run8d32": ["-DLZ_RUN_SHORT=8", "-DLZ_L6_DEPTH=32"],
+    "d16": ["-DLZ_L6_DEPTH=16"],
     # decode table geometry at the same 448 B per lane (15 warps per SM): 6-bit offset main table, 16 + 16 shared subtable entries
     "g6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16"],
     "g6b": ["-DINF_LSUB_SM=0", "-DINF_OB=6", "-DINF_OSUB_SM=32"],

@@ -428,3 +428,4 @@ def check_bgzf(ctx, sizes=(0, 1, 65279, 65280, 65281, 200000), levels=(1, 6)):
             assert ctx.bgzf_decompress(bytes(bad), n)[0] == 1      # LIBDEFLATE_BAD_DATA
             assert ctx.bgzf_decompress(gzip.compress(data), n)[0] == 1   # plain gzip has no BC subfield
             assert ctx.bgzf_decompress(ref[:-40], n)[0] == 1       # truncated
+    assert ctx.bgzf_decompress(b"", 10)[0] == 1                    # an empty file is not a gzip file

@@ -72,6 +72,15 @@ def test_gz_front_end_emulated(emu_ctx, emu_api, tmp_path):
     assert gz.decompress_bytes(emu_ctx, pc.bgzf_reference_file(data)) == data
     with pytest.raises(ValueError):
         gz.decompress_bytes(emu_ctx, gzip.compress(data))
+    # malformed size fields raise ValueError, never struct.error, and never drive a huge allocation
+    import struct
+    short_extra = bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 255]) + struct.pack("<H", 4000) + b"BC" + bytes(20)
+    with pytest.raises(ValueError):
+        gz.uncompressed_size(short_extra)
+    liar = bytearray(packed[:-28])            # drop the EOF member, then lie in the last ISIZE
+    liar[-4:] = struct.pack("<I", 0xFFFFFFF0)
+    with pytest.raises(ValueError):
+        gz.uncompressed_size(bytes(liar) * 1)
     # ordinary (not blocked) multi-member files go member by member through the classic API
     plain = gzip.compress(data[:70000], 6) + gzip.compress(b"") + gzip.compress(data[70000:], 1)
     assert gz.decompress_members(emu_api, plain) == data
