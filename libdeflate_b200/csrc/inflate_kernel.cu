@@ -82,6 +82,10 @@
 #define INF_OVF_L     (INF_LSUB_CAP - INF_LSUB_SM)	// 896 u16
 #define INF_OVF_O     (INF_OSUB_CAP - INF_OSUB_SM)	// 960 u16
 #define INF_OVF_ENTRIES (INF_OVF_L + INF_OVF_O)
+// per-lane global scratch: the overflow subtable entries, then the <= 320 code lengths of the block header
+// being parsed (written once per block by the owning lane, read once by the warp that builds the tables)
+#define INF_GS_LENS    (INF_OVF_ENTRIES * 2)
+#define INF_GS_BYTES   ((INF_GS_LENS + 320 + 127) & ~127)
 
 #ifndef INF_QUANTUM
 #define INF_QUANTUM   384		// decode steps between service phases
@@ -99,11 +103,7 @@
 #define INF_WPC        5		// independent warps per CTA
 #endif
 
-// header-parsing scratch inside the (about to be rebuilt) table slots, two bytes per u16 slot: the 320 code
-// lengths take slots 0..159 of the litlen region and, where that is shorter, run on into the offset region
-// (the two regions are adjacent and interleaved the same way); the 128-byte precode table follows them
-#define INF_SCR_PRETAB_SLOT (INF_L_ENTRIES >= 160 ? INF_L_ENTRIES : 160)	// first slot of the precode table, counted from the litlen region
-static_assert(INF_L_ENTRIES + INF_O_ENTRIES >= INF_SCR_PRETAB_SLOT + 64, "code-length scratch + precode table must fit the two table regions");
+static_assert(INF_O_ENTRIES >= 64, "the offset region doubles as the 128-byte precode table scratch");
 static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry");
 
 // entry encodings (u16)
@@ -119,7 +119,7 @@ static_assert(INF_LB >= INF_OB && INF_LB <= 10 && INF_OB >= 5, "table geometry")
 // offset is next; ST_DONE: the stream has ended with s.verdict (finished in the service phase)
 enum { ST_IDLE = 0, ST_HEADER = 1, ST_BUILD = 2, ST_STORED = 3, ST_DONE = 4, ST_LIT = 5, ST_OFF = 6 };
 
-size_t ldb_inflate_overflow_bytes_per_stream(void) { return INF_OVF_ENTRIES * sizeof(u16); }
+size_t ldb_inflate_overflow_bytes_per_stream(void) { return INF_GS_BYTES; }
 
 struct inf_lane {
 	// input: the stream is read as 4-byte aligned words; w0/w1 are the two words the
@@ -324,14 +324,14 @@ __device__ u32 inf_parse_wrapper(const u8 *in, size_t n, int format, u32 *footer
 
 // ---- per-lane header parsing ----------------------------------------------------
 // Parses one block header.  Dynamic: leaves the 320 code lengths as bytes in the
-// lane's litlen table region and moves to ST_BUILD.  Returns a verdict != SUCCESS
+// lane's global scratch and moves to ST_BUILD.  Returns a verdict != SUCCESS
 // to abort the stream.
-__device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
+__device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane, u8 *lens)
 {
-	// scratch inside the lane's own (about to be rebuilt) table slots, two bytes per u16 slot:
-	// <= 320 code lengths in the litlen region, the 128-entry precode table in the offset region
-	u8 *lens = sm + INF_SM_LTAB;		// scr_idx(i, lane)
-	u8 *pretab = sm + INF_SM_LTAB + INF_SCR_PRETAB_SLOT * 64;	// scr_idx(i, lane); a slot row is 32 lanes x 2 bytes
+	// the 128-entry precode table sits in the lane's own (about to be rebuilt) offset-table slots, two bytes
+	// per u16 slot; the code lengths go to the lane's global scratch (a block header is parsed once per ~10 K
+	// symbols: its stores cost nothing, and shared memory per lane is what limits the warps per SM)
+	u8 *pretab = sm + INF_SM_OTAB;		// scr_idx(i, lane)
 	static const u8 perm[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 	s.is_final = inf_take(s, 1);
@@ -393,7 +393,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 			s.bitpos += e & 7;
 			u32 presym = e >> 3;
 			if (presym < 16) {
-				lens[scr_idx(i, lane)] = (u8)presym;
+				lens[i] = (u8)presym;
 				prev = presym;
 				i++;
 				continue;
@@ -412,7 +412,7 @@ __device__ int inf_parse_block_header(inf_lane &s, u8 *sm, u32 lane)
 			}
 			// running past the announced count is an error (decompress_template.h:245)
 			if (i + rep > total) return LDB_BAD_DATA;
-			for (u32 k = 0; k < rep; k++) lens[scr_idx(i + k, lane)] = (u8)val;
+			for (u32 k = 0; k < rep; k++) lens[i + k] = (u8)val;
 			prev = val;
 			i += rep;
 		}
@@ -734,14 +734,18 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 // The warps of a CTA are independent (each has its own tables and never syncs with the others);
 // INF_WPC of them share a CTA only because shared memory is reserved per CTA (1 KiB each), and
 // 3 CTAs x 5 warps fit where 15 single-warp CTAs would not.
-__global__ void __launch_bounds__(32 * INF_WPC)
+#ifndef INF_MIN_CTAS
+#define INF_MIN_CTAS 3		// CTAs per SM the register allocation must allow
+#endif
+__global__ void __launch_bounds__(32 * INF_WPC, INF_MIN_CTAS)
 ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 {
 	LDB_DYN_SMEM(sm_cta);
 	u8 *sm = sm_cta + (threadIdx.x >> 5) * INF_SM_BYTES;
 	const u32 lane = threadIdx.x & 31;
 	const size_t gwarp = (size_t)blockIdx.x * INF_WPC + (threadIdx.x >> 5);	// global warp index
-	u16 *ovf = (u16 *)(a.overflow_scratch + 256) + (gwarp * 32 + lane) * INF_OVF_ENTRIES;
+	u8 *gs_lane = a.overflow_scratch + 256 + (gwarp * 32 + lane) * (size_t)INF_GS_BYTES;
+	u16 *ovf = (u16 *)gs_lane;
 
 	inf_lane s;
 	s.state = ST_IDLE;
@@ -849,7 +853,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 
 			// (2) block headers, parsed by their own lanes
 			if (s.state == ST_HEADER) {
-				int v = inf_parse_block_header(s, sm, lane);
+				int v = inf_parse_block_header(s, sm, lane, gs_lane + INF_GS_LENS);
 				if (v != LDB_SUCCESS) { s.verdict = (u32)v; s.state = ST_DONE; }
 			}
 			__syncwarp();
@@ -886,17 +890,17 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 				u32 hlit = __shfl_sync(LDB_FULL_MASK, s.hlit, owner);
 				u32 hdist = __shfl_sync(LDB_FULL_MASK, s.hdist, owner);
 				u32 is_static = __shfl_sync(LDB_FULL_MASK, s.is_static, owner);
-				const u8 *lens = sm + INF_SM_LTAB;
+				const u8 *lens = a.overflow_scratch + 256 + (gwarp * 32 + owner) * (size_t)INF_GS_BYTES + INF_GS_LENS;
 				u32 ll[9], ol[1];
 #pragma unroll
 				for (int r = 0; r < 9; r++) {
 					u32 sym = r * 32 + lane;
 					ll[r] = is_static ? inf_static_litlen_len(sym)
-							  : (sym < hlit ? lens[scr_idx(sym, owner)] : 0);
+							  : (sym < hlit ? lens[sym] : 0);
 				}
-				ol[0] = is_static ? 5u : (lane < hdist ? lens[scr_idx(hlit + lane, owner)] : 0);
+				ol[0] = is_static ? 5u : (lane < hdist ? lens[hlit + lane] : 0);
 				__syncwarp();
-				u16 *ovf_owner = (u16 *)(a.overflow_scratch + 256) + (gwarp * 32 + owner) * INF_OVF_ENTRIES;
+				u16 *ovf_owner = (u16 *)(a.overflow_scratch + 256 + (gwarp * 32 + owner) * (size_t)INF_GS_BYTES);
 				// offset code first, like the reference (decompress_template.h:331-332)
 				bool ok = inf_build_table<1, INF_OB, INF_OSUB_SM, INF_OSUB_CAP, false>(ol, sm, INF_SM_OTAB, ovf_owner + INF_OVF_L, owner, lane);
 				ok = ok && inf_build_table<9, INF_LB, INF_LSUB_SM, INF_LSUB_CAP, true>(ll, sm, INF_SM_LTAB, ovf_owner, owner, lane);

@@ -13,16 +13,13 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    # resolve kernel (32 single-warp CTAs per SM is the hardware's CTA limit)
-    # deflate kernel: half the threads per CTA (2 search runs per thread, 128 registers each)
-    "t512": ["-DLZ_THREADS=512"],
-    "run8": ["-DLZ_RUN_SHORT=8"],
-    "run8d32": ["-DLZ_RUN_SHORT=8", "-DLZ_L6_DEPTH=32"],
-    "d16": ["-DLZ_L6_DEPTH=16"],
-    # decode table geometry at the same 448 B per lane (15 warps per SM): 6-bit offset main table, 16 + 16 shared subtable entries
-    "g6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16"],
-    "g6b": ["-DINF_LSUB_SM=0", "-DINF_OB=6", "-DINF_OSUB_SM=32"],
+    # decode kernel: smaller per-lane tables -> more warps per SM (the ALU pipe is 50 % busy at 15 warps: the kernel lacks warps)
+    "w18": ["-DINF_LB=7", "-DINF_LSUB_SM=0", "-DINF_OB=5", "-DINF_OSUB_SM=32", "-DINF_WPC=6"],     # 384 B/lane, 3 x 6 warps
+    "w21": ["-DINF_LB=6", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32", "-DINF_WPC=7"],    # 320 B/lane, 3 x 7 warps
+    "w24": ["-DINF_LB=6", "-DINF_LSUB_SM=16", "-DINF_OB=5", "-DINF_OSUB_SM=32", "-DINF_WPC=8"],    # 288 B/lane, 3 x 8 warps
 }
+# deflate kernel at 16384 chunks (base 79.2 ms, ratio 0.3022): 512 threads per CTA 97.5 ms; runs of 8 positions 84.0 ms / 0.3038;
+# runs of 8 + depth 32: 90.0 / 0.3028; depth 16: 73.8 / 0.3035 -- nothing that is faster at the same ratio
 # decode kernel, offset table geometry: 6-bit main + 16 shared subtable entries at 14 warps per SM 17.5 ms (= default);
 # 13-warp geometries 27-28 ms (65536 chunks no longer fit one wave of lanes)
 # decode steps between service phases, -DINF_QUANTUM=128/384/1024: 17.4 / 17.5 / 17.6 ms
