@@ -153,6 +153,29 @@ def check_inputs_with_unmapped_gaps(ctx):
         libc.mprotect(base + 3 * page, 2 * page, 3)
 
 
+def check_decompress_in_waves(ctx, orc, n_chunks=90):
+    """The token scratch between the two inflate kernels is handed out in waves of consecutive chunks; with a 1 MB
+    budget this batch needs many of them (and one chunk is larger than the whole budget).  Same results either way."""
+    import os
+    plains = [corpus.text(20000 + 137 * i, i) if i % 4 else corpus.mixed(9000 + i, i) for i in range(n_chunks)]
+    plains[n_chunks // 2] = corpus.text(1500000, 5)
+    zs = [corpus.zlib_raw(p, 6, zlib.Z_DEFAULT_STRATEGY, 15) for p in plains]
+    zs[3] = zs[3][:len(zs[3]) // 2]                 # a truncated stream in the middle of a wave
+    old = os.environ.get("LIBDEFLATE_B200_TOKEN_BUDGET_MB")
+    os.environ["LIBDEFLATE_B200_TOKEN_BUDGET_MB"] = "1"
+    try:
+        got = ctx.decompress_batch_host(zs, [len(p) for p in plains], 1)
+    finally:
+        if old is None:
+            del os.environ["LIBDEFLATE_B200_TOKEN_BUDGET_MB"]
+        else:
+            os.environ["LIBDEFLATE_B200_TOKEN_BUDGET_MB"] = old
+    for i, (p, z, g) in enumerate(zip(plains, zs, got)):
+        o = orc.decompress(z, len(p), 1)
+        assert g[0] == o[0] and (o[0] != 0 or g == o), ("wave mismatch", i, g[0], o[0])
+    assert got[3][0] != 0 and got[4][0] == 0
+
+
 def gzip_member(plain, flg, level=6, extra=b"EXTRA-field", name=b"file name.txt", comment=b"a comment"):
     """A gzip member with the optional header fields selected by FLG (RFC 1952 2.3: FTEXT 1, FHCRC 2, FEXTRA 4,
     FNAME 8, FCOMMENT 16), built by hand around a zlib-made raw stream."""

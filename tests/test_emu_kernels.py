@@ -24,6 +24,10 @@ def test_gzip_optional_header_fields_emulated(emu_ctx, oracle, reflib):
     pc.check_gzip_optional_fields(emu_ctx, oracle, reflib)
 
 
+def test_inflate_token_scratch_waves_emulated(emu_ctx, oracle):
+    pc.check_decompress_in_waves(emu_ctx, oracle, n_chunks=40)
+
+
 def test_inflate_large_chunks_emulated(emu_ctx):
     pc.check_decompress_large(emu_ctx, sizes=(150000,), levels=(0, 6))
 

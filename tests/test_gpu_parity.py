@@ -145,6 +145,10 @@ def test_two_devices_one_process():
     assert outs[0] == outs[1] == outs[2]
 
 
+def test_decompress_token_scratch_waves(gpu_ctx, oracle):
+    pc.check_decompress_in_waves(gpu_ctx, oracle, n_chunks=400)
+
+
 def test_decompress_large_chunks(gpu_ctx):
     pc.check_decompress_large(gpu_ctx)
 
