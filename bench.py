@@ -189,7 +189,7 @@ def run_reference(args):
     chunk = args.chunk_size
     n = args.chunks
     buf = (ctypes.c_uint8 * (n * chunk))()
-    synth.synth_fill(buf, chunk, 0, n, 0, threads)
+    synth.synth_fill(buf, chunk, 0, n, getattr(args, "data_class", 0), threads)
     fmt = 2 if args.workload == "roundtrip" else 0
     times = []
     ratio = None
@@ -386,7 +386,7 @@ def run_b200(args):
     pin_in = l.libdeflate_b200_pinned_malloc(n * chunk)
     assert pin_in, "pinned_malloc failed"
     first_chunk, _ = shard.shard_range(rank, world, n)
-    synth.synth_fill(pin_in, chunk, first_chunk, n, 0, threads)
+    synth.synth_fill(pin_in, chunk, first_chunk, n, getattr(args, "data_class", 0), threads)
     d_in = DeviceBatch(ctx, n, chunk)
     ctx._check(l.libdeflate_b200_memcpy_h2d(ctx.h, d_in.slab, pin_in, n * chunk), "h2d")
     d_in.set_sizes(np.full(n, chunk, dtype=np.uint64))
@@ -620,7 +620,7 @@ def run_b200(args):
         if rank == 0:
             root_in = torch.empty(n_total * chunk, dtype=torch.uint8, device=dev)
             for r in range(world):        # the batch of the pre-sharded run, rank by rank, through the one pinned buffer
-                synth.synth_fill(pin_in, chunk, r * n, n, 0, threads)
+                synth.synth_fill(pin_in, chunk, r * n, n, getattr(args, "data_class", 0), threads)
                 ctx._check(l.libdeflate_b200_memcpy_h2d(ctx.h, root_in.data_ptr() + r * n * chunk, pin_in, n * chunk), "h2d")
                 ctx.sync()
         so_steps = max(1, min(args.steps, 2))
@@ -649,7 +649,8 @@ def run_b200(args):
     line = {
         "metric": metric_name(args), "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
         "steps": steps, "warmup": args.warmup, "ms_per_step": round(ms_max / steps, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic" if getattr(args, "data_class", 0) == 0 else "synthetic (class %d of bench/synth.c, not the headline corpus)" % args.data_class,
         "config": workload_config(args),
         "roofline": dominant, "roofline_inflate": r_inf_north or r_inf, "roofline_deflate": r_def,
         "kernel_ms_per_step": {k: round(v[0] / steps, 4) for k, v in ktime.items() if v[1]},
@@ -756,6 +757,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=NCHUNKS_DEFAULT)
     ap.add_argument("--chunk-size", type=int, default=CHUNK_DEFAULT)
     ap.add_argument("--level", type=int, default=LEVEL, help="compression level (BASELINE configs[3] uses 12 with --chunk-size 1048576 --chunks 4096)")
+    ap.add_argument("--data-class", type=int, default=0, help="synthetic chunk class (bench/synth.c): 0 text (the headline corpus), 1 pattern, 2 stride, 3 random, 4 zeros, 5 mixed, 6 all of them in turn")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short legs of the other BASELINE configs (decompress-only, checksums, level 12)")
