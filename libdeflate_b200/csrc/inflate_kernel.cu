@@ -87,6 +87,15 @@
 #define INF_GS_LENS    (INF_OVF_ENTRIES * 2)
 #define INF_GS_BYTES   ((INF_GS_LENS + 320 + 127) & ~127)
 
+// the token stream is written once here and read once by the next kernel: cache-streaming stores
+#ifndef INF_STREAM_HINTS
+#define INF_STREAM_HINTS 1
+#endif
+#if INF_STREAM_HINTS
+#define INF_ST_TOK(p, v) __stcs((p), (v))
+#else
+#define INF_ST_TOK(p, v) (*(p) = (v))
+#endif
 #ifndef INF_QUANTUM
 #define INF_QUANTUM   384		// decode steps between service phases
 #endif
@@ -710,7 +719,7 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	const u32 acc2 = __funnelshift_r(s.acc, e >> 4, 8);
 	s.acc = put ? acc2 : s.acc;
 	s.n_lit += put ? 1u : 0u;
-	if (put && (s.n_lit & 3) == 0) *(u32 *)(s.lit + s.n_lit - 4) = s.acc;
+	if (put && (s.n_lit & 3) == 0) INF_ST_TOK((u32 *)(s.lit + s.n_lit - 4), s.acc);
 	// length or offset: base(slot) + extra bits, the same arithmetic up to k
 	const u32 vbits = bits >> cl;
 	const u32 slot = (e >> 4) & 31;
@@ -736,8 +745,8 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	const bool big = litrun > 255;
 	if (emit) {
 		u32 *r = s.rec_end - s.n_rec - 1;
-		if (big) { *r = LDB_TOK_PURE_FLAG | litrun; r--; }
-		*r = ((big ? 0u : litrun) << 23) | ((s.pend_len - 3) << 15) | (val - 1);
+		if (big) { INF_ST_TOK(r, LDB_TOK_PURE_FLAG | litrun); r--; }
+		INF_ST_TOK(r, ((big ? 0u : litrun) << 23) | ((s.pend_len - 3) << 15) | (val - 1));
 	}
 	s.n_rec += emit ? (big ? 2u : 1u) : 0u;
 	s.lit_mark = emit ? s.n_lit : s.lit_mark;

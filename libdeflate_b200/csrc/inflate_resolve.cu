@@ -38,6 +38,16 @@
 #define RES_LIT_FAST 16u	// literal runs up to this are placed by the owning lane in one step
 #endif
 #define RES_SM_BYTES RES_STG
+// token records are read exactly once: cache-streaming loads (evict-first) keep them from displacing the
+// window rows in L2
+#ifndef RES_STREAM_HINTS
+#define RES_STREAM_HINTS 1
+#endif
+#if RES_STREAM_HINTS
+#define RES_LD_REC(p) __ldcs(p)
+#else
+#define RES_LD_REC(p) __ldg(p)
+#endif
 #ifndef RES_PER_SM
 #define RES_PER_SM  32		// warps (= chunks) per SM; measured 8 / 16 / 24 / 32: 25.9 / 14.2 / 10.6 / 9.0 ms per 4 GiB
 #endif
@@ -235,9 +245,9 @@ ldb_inflate_resolve_kernel(ldb_inflate_args a, u32 *work_counter)
 			const bool valid = i < n_rec;
 			u32 r = LDB_TOK_PURE_FLAG;
 			if (next_r0 == r0) r = r_next;
-			else if (valid) r = __ldg(rec_end - 1 - (s32)i);
+			else if (valid) r = RES_LD_REC(rec_end - 1 - (s32)i);
 			next_r0 = r0 + 32;
-			r_next = (i + 32 < n_rec) ? __ldg(rec_end - 1 - (s32)(i + 32)) : LDB_TOK_PURE_FLAG;
+			r_next = (i + 32 < n_rec) ? RES_LD_REC(rec_end - 1 - (s32)(i + 32)) : LDB_TOK_PURE_FLAG;
 			u32 lits, mlen = 0, off = 0;
 			if (r & LDB_TOK_PURE_FLAG) {
 				lits = r & 0x7fffffffu;

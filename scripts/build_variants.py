@@ -13,11 +13,12 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    # decode kernel: smaller per-lane tables -> more warps per SM (the ALU pipe is 50 % busy at 15 warps: the kernel lacks warps)
-    "w18": ["-DINF_LB=7", "-DINF_LSUB_SM=0", "-DINF_OB=5", "-DINF_OSUB_SM=32", "-DINF_WPC=6"],     # 384 B/lane, 3 x 6 warps
-    "w21": ["-DINF_LB=6", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32", "-DINF_WPC=7"],    # 320 B/lane, 3 x 7 warps
-    "w24": ["-DINF_LB=6", "-DINF_LSUB_SM=16", "-DINF_OB=5", "-DINF_OSUB_SM=32", "-DINF_WPC=8"],    # 288 B/lane, 3 x 8 warps
+    # cache hints off (the default build streams the token stream through L2 with evict-first loads / stores)
+    "nohint": ["-DRES_STREAM_HINTS=0", "-DINF_STREAM_HINTS=0"],
+    "r24": ["-DRES_PER_SM=24"],
 }
+# decode kernel with more warps per SM (code lengths in global memory, smaller tables, register cap): 18 / 21 / 24 warps
+# 20.8 / 18.6 / 17.1 ms vs 16.7 ms at 15 warps -- dropped
 # deflate kernel at 16384 chunks (base 79.2 ms, ratio 0.3022): 512 threads per CTA 97.5 ms; runs of 8 positions 84.0 ms / 0.3038;
 # runs of 8 + depth 32: 90.0 / 0.3028; depth 16: 73.8 / 0.3035 -- nothing that is faster at the same ratio
 # decode kernel, offset table geometry: 6-bit main + 16 shared subtable entries at 14 warps per SM 17.5 ms (= default);
