@@ -97,6 +97,9 @@ LIBDEFLATEAPI uint64_t libdeflate_b200_launch_count(struct libdeflate_b200_ctx *
  * LIBDEFLATE_B200_EXACT_OUT_SIZE a chunk that decodes to fewer than
  * out_avail[i] bytes gets LIBDEFLATE_SHORT_OUTPUT.  A bad chunk never aborts the
  * batch.  For gzip/zlib the checksum of the output is verified on the device.
+ * Limits: per-chunk sizes are handled as 32-bit on the device -- in_nbytes and out_avail above
+ * 4 GiB - 16 are clamped, so a single stream that large is not supported (cut such data into chunks,
+ * e.g. with libdeflate_b200_bgzf_*); the reference's size_t API has no such limit.
  */
 LIBDEFLATEAPI int
 libdeflate_b200_decompress_batch(struct libdeflate_b200_ctx *ctx, int format, unsigned flags,
