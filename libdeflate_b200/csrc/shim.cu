@@ -602,6 +602,21 @@ static host_span span_of(const void *const *ptrs, const size_t *sizes, size_t n,
 	return s;
 }
 
+// Leaves no copy into caller memory in flight, whatever path the function returns on (the CUDA error
+// checks return early from inside the sub-batch loops).
+struct stream_quiesce {
+	libdeflate_b200_ctx *ctx;
+	explicit stream_quiesce(libdeflate_b200_ctx *c) : ctx(c) {}
+	~stream_quiesce()
+	{
+		if (ctx->stream_h2d) cudaStreamSynchronize(ctx->stream_h2d);
+		if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+		if (ctx->stream_d2h) cudaStreamSynchronize(ctx->stream_d2h);
+	}
+	stream_quiesce(const stream_quiesce &) = delete;
+	stream_quiesce &operator=(const stream_quiesce &) = delete;
+};
+
 struct staged_batch {
 	void **d_ptrs;		// device array of device pointers
 	size_t *d_sizes;	// device array
@@ -730,6 +745,7 @@ static int ldb_decompress_batch_host_impl(struct libdeflate_b200_ctx *ctx, int f
 {
 	if (n == 0) return 0;
 	cudaSetDevice(ctx->device);
+	stream_quiesce quiesce(ctx);
 	// parameter block: in ptrs/sizes | out ptrs/sizes | actual_in | actual_out | results
 	size_t pb = param_block_bytes(n);
 	size_t res_off = 2 * pb;
@@ -873,6 +889,7 @@ extern "C" int libdeflate_b200_compress_batch_host_packed(struct libdeflate_b200
 	if (n == 0) return 0;
 	if (format < LDB_FMT_RAW || format > LDB_FMT_GZIP) return ldb_fail(cudaErrorInvalidValue, "format", __FILE__, __LINE__);
 	LDB_CUDA_CHECK_RET(cudaSetDevice(ctx->device));
+	stream_quiesce quiesce(ctx);
 	// device slots: one per chunk, compress_bound() rounded up to 16
 	host_scratch slot_own((n + 1) * sizeof(size_t));
 	size_t *slot_off = (size_t *)slot_own.p;
@@ -979,6 +996,7 @@ extern "C" int libdeflate_b200_compress_batch_host(struct libdeflate_b200_ctx *c
 {
 	if (n == 0) return 0;
 	cudaSetDevice(ctx->device);
+	stream_quiesce quiesce(ctx);
 	size_t pb = param_block_bytes(n);
 	size_t res_off = 2 * pb;
 	size_t res_bytes = align_up(n * sizeof(size_t), 256);

@@ -16,6 +16,7 @@ VARIANTS = {
     # cache hints off (the default build streams the token stream through L2 with evict-first loads / stores)
     "nohint": ["-DRES_STREAM_HINTS=0", "-DINF_STREAM_HINTS=0"],
     "r24": ["-DRES_PER_SM=24"],
+    "timing": ["-DLZ_TIMING"],      # per-phase cycle counters of the deflate kernel (prints at exit of scripts/variant_bench.py)
 }
 # decode kernel with more warps per SM (code lengths in global memory, smaller tables, register cap): 18 / 21 / 24 warps
 # 20.8 / 18.6 / 17.1 ms vs 16.7 ms at 15 warps -- dropped
