@@ -107,7 +107,8 @@
 #define INF_SM_CNT     (INF_SM_SCRATCH)				// u32[16]
 #define INF_SM_CODE    (INF_SM_CNT + 64)			// u32[16]
 #define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[1 << INF_LB]
-#define INF_SM_BYTES   (INF_SM_SUBBITS + (1 << INF_LB))		// per warp: 14592 with the default geometry
+#define INF_SM_WQ      (INF_SM_SUBBITS + (1 << INF_LB))		// u32[32]: per-lane prefetched input word of the decode loop
+#define INF_SM_BYTES   (INF_SM_WQ + 128)				// per warp: 14720 with the default geometry
 #ifndef INF_WPC
 #define INF_WPC        5		// independent warps per CTA
 #endif
@@ -171,6 +172,20 @@ struct inf_lane {
 __device__ __forceinline__ u32 tab_idx(u32 entry, u32 lane) { return entry * 32 + lane; }
 // byte i of a lane's scratch: low/high byte of the lane's u16 slot i/2
 __device__ __forceinline__ u32 scr_idx(u32 i, u32 lane) { return ((i >> 1) * 32 + lane) * 2 + (i & 1); }
+
+// ---- asynchronous 4-byte global -> shared copy (LDGSTS): the prefetch of the next input word goes through
+// shared memory so that no register -- and therefore no scoreboard wait of the whole warp -- is tied to
+// the load until the word is needed, ~3 steps later
+#ifndef LDB_EMU
+__device__ __forceinline__ void inf_cp_async4(u32 *smem_dst, const void *gsrc)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void inf_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+__device__ __forceinline__ void inf_cp_async4(u32 *smem_dst, const void *gsrc) { *smem_dst = *(const u32 *)gsrc; }
+__device__ __forceinline__ void inf_cp_async_wait() {}
+#endif
 
 // ---- bit reader ---------------------------------------------------------------
 __device__ __forceinline__ u32 inf_ld_word(const inf_lane &s, u32 pos)
@@ -663,6 +678,15 @@ __device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
 	return sym < 144 ? 8 : (sym < 256 ? 9 : (sym < 280 ? 7 : 8));
 }
 
+#if defined(LDB_EMU) && defined(INF_STATS)
+// tuning aid of the emulator build only: {litlen sub in smem, litlen sub global, offset sub in smem, offset sub global, steps}
+unsigned long long inf_stats[8];
+extern "C" __attribute__((visibility("default"))) void ldb_inf_stats(unsigned long long *out, int reset)
+{
+	for (int i = 0; i < 8; i++) { out[i] = inf_stats[i]; if (reset) inf_stats[i] = 0; }
+}
+#endif
+
 // ---- decoding: ONE step function for both alphabets -------------------------------------------
 // A lane is either about to read a litlen symbol (ST_LIT) or the offset symbol of a pending length
 // (ST_OFF).  Both are "look up table[bits & mask], maybe a subtable, consume the codeword"; a length
@@ -673,22 +697,17 @@ __device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
 // what counts is the number of instructions per step.
 // The stream ends by moving to ST_DONE with a verdict; the bookkeeping of a finished stream
 // happens once per service phase, outside this loop.
-__device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane)
+__device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const u16 *ovf, u32 lane, u32 *wq)
 {
 	// Written as ONE predicated block (selects instead of branches, stores under a predicate, no early
 	// returns): with ~31 of 32 lanes active every path is taken by somebody in every step anyway, so
 	// branches only add reconvergence bookkeeping and register shuttling at the merge points.
 	const bool act = s.state >= ST_LIT;
 	const bool isoff = s.state == ST_OFF;
-	// refill (bitpos < 32 afterwards)
-	const bool rf = act && s.bitpos >= 32;
-	u32 nw = s.w2;
-	if (rf) nw = inf_ld_word(s, s.wpos + 12);
-	s.w0 = rf ? s.w1 : s.w0;
-	s.w1 = rf ? s.w2 : s.w1;
-	s.w2 = nw;
-	s.wpos += rf ? 4u : 0u;
-	s.bitpos -= rf ? 32u : 0u;
+#if defined(LDB_EMU) && defined(INF_STATS)
+	if (act) atomicAdd(&inf_stats[4 + (isoff ? 1 : 0)], 1ull);
+#endif
+	// (bitpos < 32 here: the window is refilled at the END of a step, see below)
 	u32 bits = __funnelshift_r(s.w0, s.w1, s.bitpos);
 	// start of a litlen symbol with virtual zero bytes (nearly) in play: P >= 8n+9 means the reference's
 	// refill over-read more than sizeof(bitbuf) bytes (deflate_decompress.c:236-254)
@@ -707,6 +726,9 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 		const u32 idx = sstart + (bits & ((1u << sb) - 1));
 		const u32 sub_sm = isoff ? INF_OSUB_SM : INF_LSUB_SM;
 		e = idx < sub_sm ? tab[((1u << mainbits) + idx) * 32] : ovf[(isoff ? INF_OVF_L : 0) + idx - sub_sm];
+#if defined(LDB_EMU) && defined(INF_STATS)
+		atomicAdd(&inf_stats[(isoff ? 2 : 0) + (idx < sub_sm ? 0 : 1)], 1ull);	// tuning: where do subtable lookups go
+#endif
 	}
 	const u32 cl = e & 15;
 	adv += cl;
@@ -766,6 +788,21 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	vd = dead ? (u32)LDB_BAD_DATA : vd;
 	s.state = st;
 	s.verdict = vd;
+	// refill for the NEXT step (bitpos < 32 afterwards).  Inside the decode loop the third window word lives
+	// in the lane's shared-memory slot wq: the next word is fetched into it by an asynchronous copy, so the
+	// load is tied to no register (held in a register, the compiler copied the word being loaded into the
+	// loop-carried register at the bottom of the loop and every step waited there: 10 % of the stall samples).
+	const bool rf = act && s.bitpos >= 32;
+	if (rf) {
+		inf_cp_async_wait();			// the word asked for ~3 steps ago
+		s.w0 = s.w1;
+		s.w1 = *(volatile u32 *)wq;
+		s.wpos += 4;
+		s.bitpos -= 32;
+		const u32 pos = s.wpos + 8;
+		if (pos + 4 <= s.in_nal) inf_cp_async4(wq, s.in_al + pos);
+		else *(volatile u32 *)wq = inf_ld_word(s, pos);	// ragged end of the input: zero-padded word
+	}
 }
 
 // ---- the decode kernel --------------------------------------------------------------
@@ -945,7 +982,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 				__threadfence_block();
 				if (lane == owner) {
 					if (!ok) { s.verdict = LDB_BAD_DATA; s.state = ST_DONE; }
-					else s.state = ST_LIT;
+					else { s.state = ST_LIT; (void)inf_peek(s); }	// the decode step expects bitpos < 32
 				}
 			}
 			__syncwarp();
@@ -956,10 +993,14 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 
 		// ---- decode phase: INF_QUANTUM steps, one symbol per lane and step ---------------------
 #pragma unroll 1
+		u32 *wq = (u32 *)(sm + INF_SM_WQ) + lane;
+		*(volatile u32 *)wq = s.w2;		// inside the loop the third window word lives in shared memory
 		for (int it = 0; it < INF_QUANTUM; it++) {
-			inf_decode_step(s, sm, ovf, lane);
+			inf_decode_step(s, sm, ovf, lane, wq);
 			if ((it & 31) == 31 && !__any_sync(LDB_FULL_MASK, s.state >= ST_LIT)) break;
 		}
+		inf_cp_async_wait();
+		s.w2 = *(volatile u32 *)wq;		// ... and outside of it in a register again
 		__syncwarp();
 	}
 }

@@ -13,11 +13,12 @@ GEO_G = ["-DINF_LB=7", "-DINF_LSUB_SM=96", "-DINF_OB=6", "-DINF_OSUB_SM=64"]    
 GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 512 B, 13 warps
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
-    # cache hints off (the default build streams the token stream through L2 with evict-first loads / stores)
-    "nohint": ["-DRES_STREAM_HINTS=0", "-DINF_STREAM_HINTS=0"],
-    "r24": ["-DRES_PER_SM=24"],
-    "timing": ["-DLZ_TIMING"],      # per-phase cycle counters of the deflate kernel (prints at exit of scripts/variant_bench.py)
+    # decode table geometries at 448 B per lane (offline count of global overflow lookups per lane-step on the bench corpus:
+    # default 0.35 %, g6 0.20 %, o5s48l16 0.22 %)
+    "g6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16"],
+    "o5s48l16": ["-DINF_LSUB_SM=16", "-DINF_OB=5", "-DINF_OSUB_SM=48"],
 }
+# cache-streaming hints for the token stream off / 24 resolve warps per SM: no change / 10.5 ms (default 9.0)
 # decode kernel with more warps per SM (code lengths in global memory, smaller tables, register cap): 18 / 21 / 24 warps
 # 20.8 / 18.6 / 17.1 ms vs 16.7 ms at 15 warps -- dropped
 # deflate kernel at 16384 chunks (base 79.2 ms, ratio 0.3022): 512 threads per CTA 97.5 ms; runs of 8 positions 84.0 ms / 0.3038;
