@@ -713,23 +713,90 @@ def run_e2e(args, ctx, l, ldb, pin_in, n, chunk, fmt, cstride, barrier, allmax, 
                                                                     pin_comp, packed_cap, comp_offs.ctypes.data, comp_sizes.ctypes.data), "compress_batch_host_packed")
         ctx._check(l.libdeflate_b200_decompress_batch_host_packed(ctx.h, fmt, 0, pin_comp, comp_offs.ctypes.data, comp_sizes.ctypes.data, ne,
                                                                   out_ptrs.ctypes.data, out_avail.ctypes.data, None, aout.ctypes.data, res.ctypes.data), "decompress_batch_host_packed")
-    for _ in range(min(args.warmup, 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    ksteps = max(1, min(args.steps, 3))
-    for _ in range(ksteps):
-        e2e_step()
-    dt = time.perf_counter() - t0
-    dt = allmax(dt)
-    assert (res == 0).all() and (aout == chunk).all()
     host_in = np.ctypeslib.as_array(ctypes.cast(pin_in, ctypes.POINTER(ctypes.c_uint8)), shape=(ne * chunk,))
     host_out = np.ctypeslib.as_array(ctypes.cast(pin_out, ctypes.POINTER(ctypes.c_uint8)), shape=(ne * chunk,))
-    assert np.array_equal(host_in, host_out), "e2e round trip mismatch"
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    val = world * ne * chunk * ksteps / 1e6 / dt
+    ksteps = max(1, min(args.steps, 3))
+
+    def measure(step):
+        for _ in range(min(args.warmup, 2)):
+            step()
+        res[:] = -1
+        aout[:] = 0
+        host_out[:4096] = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            step()
+        dt = allmax(time.perf_counter() - t0)
+        assert (res == 0).all() and (aout == chunk).all()
+        assert np.array_equal(host_in, host_out), "e2e round trip mismatch"
+        return world * ne * chunk * ksteps / 1e6 / dt
+
+    val = measure(e2e_step)
     comp_total = int(comp_sizes.sum())
     packed_total = int(comp_offs[ne])
+    mode = "one host thread: compress call, then decompress call, whole batch each"
+    serial_val, groups, two_thread_val = val, 0, None
+    if args.workload == "roundtrip" and ne >= int(os.environ.get("LDB_E2E_GROUP_MIN", "4096")) and getattr(args, "overlap", False):
+        # The same two calls with the batch going through in GROUPS: one host thread compresses group g + 1 (own
+        # context = own stream) while a second one decompresses group g, to hide the decompress call's PCIe time
+        # behind the deflate kernel of the next group.  Measured: it does not pay (profiles/r02_e2e_overlap.md).
+        import threading
+        groups = 4
+        ng = ne // groups
+        ctx2 = ldb.Context(ctx.device, l)
+        gcap = ng * (cstride + 16)
+        g_offs = [np.zeros(ng + 1, dtype=np.uint64) for _ in range(groups)]
+        g_sizes = [np.zeros(ng, dtype=np.uint64) for _ in range(groups)]
+
+        trace = [] if os.environ.get("LDB_E2E_TRACE") else None
+
+        def overlapped_step():
+            done = [threading.Event() for _ in range(groups)]
+            err = []
+            t_base = time.perf_counter()
+            if trace is not None:
+                trace.clear()
+
+            def comp():
+                try:
+                    for g in range(groups):
+                        lo = g * ng
+                        ctx._check(l.libdeflate_b200_compress_batch_host_packed(ctx.h, fmt, LEVEL, in_ptrs[lo:].ctypes.data, in_sizes[lo:].ctypes.data, ng,
+                                                                                pin_comp + g * gcap, gcap, g_offs[g].ctypes.data, g_sizes[g].ctypes.data), "compress_batch_host_packed")
+                        if trace is not None:
+                            trace.append(("compress %d done" % g, round(1e3 * (time.perf_counter() - t_base), 1)))
+                        done[g].set()
+                except Exception as e:      # noqa: BLE001
+                    err.append(e)
+                    for d in done:
+                        d.set()
+            t = threading.Thread(target=comp)
+            t.start()
+            for g in range(groups):
+                done[g].wait()
+                if err:
+                    break
+                lo = g * ng
+                ctx2._check(l.libdeflate_b200_decompress_batch_host_packed(ctx2.h, fmt, 0, pin_comp + g * gcap, g_offs[g].ctypes.data, g_sizes[g].ctypes.data, ng,
+                                                                           out_ptrs[lo:].ctypes.data, out_avail[lo:].ctypes.data, None, aout[lo:].ctypes.data, res[lo:].ctypes.data),
+                            "decompress_batch_host_packed")
+                if trace is not None:
+                    trace.append(("decompress %d done" % g, round(1e3 * (time.perf_counter() - t_base), 1)))
+            t.join()
+            if err:
+                raise err[0]
+        if ng * groups == ne:
+            oval = measure(overlapped_step)
+            assert sum(int(z.sum()) for z in g_sizes) == comp_total      # the same streams as the one-call form
+            two_thread_val = oval
+            if trace:
+                print("e2e two-thread timeline of the last step (ms):", sorted(trace, key=lambda t: t[1]), file=sys.stderr)
+            if oval > val:
+                val = oval
+                mode = "two host threads, %d groups of %d chunks: compressing group g+1 overlaps decompressing group g" % (groups, ng)
+        ctx2.close()
     small = 16 * ne + 8 * (ne + 1)      # size / offset tables
     if args.workload == "roundtrip":
         h2d = ne * chunk + packed_total + small
@@ -741,6 +808,7 @@ def run_e2e(args, ctx, l, ldb, pin_in, n, chunk, fmt, cstride, barrier, allmax, 
     l.libdeflate_b200_pinned_free(pin_out)
     return {"value": round(val, 2), "unit": "MB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "payload_compressed_bytes": comp_total, "packed_compressed_bytes": packed_total, "chunks_per_gpu": ne, "steps": ksteps,
+            "mode": mode, "one_thread_value": round(serial_val, 2), "two_thread_value": None if two_thread_val is None else round(two_thread_val, 2),
             "api": "libdeflate_b200_compress_batch_host_packed + libdeflate_b200_decompress_batch_host_packed" if args.workload == "roundtrip"
                    else "libdeflate_b200_decompress_batch_host_packed",
             "timing": "host wall clock around the synchronous host calls, max over ranks"}
@@ -762,6 +830,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short legs of the other BASELINE configs (decompress-only, checksums, level 12)")
     ap.add_argument("--no-l12", action="store_true", help="skip the level-12 4096 x 1 MiB leg")
+    ap.add_argument("--overlap", action="store_true", help="e2e: also measure the two-host-thread form (compress of group g+1 over decompress of group g); "
+                    "measured slower than the plain form (9.3 vs 10.06 GB/s, profiles/r02_e2e_overlap.md), hence off by default")
     ap.add_argument("--no-origin", action="store_true", help="N > 1: skip the single-origin (NCCL scatter/gather) leg")
     args = ap.parse_args()
     LEVEL = args.level

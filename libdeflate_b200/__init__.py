@@ -245,6 +245,7 @@ class Context:
 
     def __init__(self, device=0, library=None):
         self.l = library or lib()
+        self.device = device
         self.h = self.l.libdeflate_b200_ctx_create(device)
         if not self.h:
             raise Error("libdeflate_b200_ctx_create(%d) failed: %s (no CPU fallback exists)"
