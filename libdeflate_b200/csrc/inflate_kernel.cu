@@ -107,6 +107,9 @@
 #define INF_SM_CNT     (INF_SM_SCRATCH)				// u32[16]
 #define INF_SM_CODE    (INF_SM_CNT + 64)			// u32[16]
 #define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[1 << INF_LB]
+#ifndef INF_LIT2
+#define INF_LIT2 1		// decode a second literal in the same step when two follow each other
+#endif
 #define INF_SM_WQ      (INF_SM_SUBBITS + (1 << INF_LB))		// u32[32]: per-lane prefetched input word of the decode loop
 #define INF_SM_BYTES   (INF_SM_WQ + 128)				// per warp: 14720 with the default geometry
 #ifndef INF_WPC
@@ -742,8 +745,24 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	s.acc = put ? acc2 : s.acc;
 	s.n_lit += put ? 1u : 0u;
 	if (put && (s.n_lit & 3) == 0) INF_ST_TOK((u32 *)(s.lit + s.n_lit - 4), s.acc);
-	// length or offset: base(slot) + extra bits, the same arithmetic up to k
 	const u32 vbits = bits >> cl;
+#if INF_LIT2
+	// A second literal in the same step: 72 % of the bench corpus' symbols are literals and they come in
+	// runs, so after a literal the next main-table entry is looked up at once and taken if it is a plain
+	// literal too (<= INF_LB bits, at least 17 valid bits are left in 'vbits').  Not near the end of the
+	// input (the tail rule above is evaluated per symbol start) and not when the output is full: those
+	// cases take the next step.
+	{
+		const u32 e2 = ((const u16 *)(sm + INF_SM_LTAB) + lane)[(vbits & ((1u << INF_LB) - 1)) * 32];
+		const bool put2 = put && e2 < LE_LEN_FLAG && s.wpos + 8 <= s.in_nal && s.n_lit != s.lit_limit;
+		const u32 acc3 = __funnelshift_r(s.acc, e2 >> 4, 8);
+		s.acc = put2 ? acc3 : s.acc;
+		s.n_lit += put2 ? 1u : 0u;
+		if (put2 && (s.n_lit & 3) == 0) INF_ST_TOK((u32 *)(s.lit + s.n_lit - 4), s.acc);
+		adv += put2 ? (e2 & 15) : 0u;
+	}
+#endif
+	// length or offset: base(slot) + extra bits, the same arithmetic up to k
 	const u32 slot = (e >> 4) & 31;
 	const u32 k = isoff ? 1 : 2;			// slots per doubling = 1 << k
 	const u32 first = 2u << k;			// first slot with extra bits: 4 (offsets), 8 (lengths)

@@ -14,9 +14,9 @@ GEO_C = ["-DINF_LB=7", "-DINF_LSUB_SM=64", "-DINF_OB=5", "-DINF_OSUB_SM=32"]    
 GEO_D = ["-DINF_LB=7", "-DINF_LSUB_SM=32", "-DINF_OB=5", "-DINF_OSUB_SM=32"]      # 448 B, 15 warps
 VARIANTS = {
     # decode table geometries at 448 B per lane (offline count of global overflow lookups per lane-step on the bench corpus:
-    # default 0.35 %, g6 0.20 %, o5s48l16 0.22 %)
-    "g6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16"],
-    "o5s48l16": ["-DINF_LSUB_SM=16", "-DINF_OB=5", "-DINF_OSUB_SM=48"],
+    # default 0.35 %, g6 0.20 %, o5s48l16 0.22 %): g6 = -DINF_LSUB_SM=16 -DINF_OB=6 -DINF_OSUB_SM=16 16.73 ms,
+    # o5s48l16 = -DINF_LSUB_SM=16 -DINF_OB=5 -DINF_OSUB_SM=48 16.68 ms vs 16.54 ms default -- dropped
+    "timing": ["-DLZ_TIMING"],          # in-kernel phase clocks of the deflate kernel (ldb_lz_timing_dump)
 }
 # cache-streaming hints for the token stream off / 24 resolve warps per SM: no change / 10.5 ms (default 9.0)
 # decode kernel with more warps per SM (code lengths in global memory, smaller tables, register cap): 18 / 21 / 24 warps

@@ -1,0 +1,6 @@
+# round 2, call S: decode takes a second literal in the same step
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x -k "decompress or inflate or fixture or known or gzip or reference_test" > gpurun_out/s_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/s_pytest.log
+timeout 600 python bench.py --workload decompress --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/s_bench_dec.json 2> gpurun_out/s_bench_dec.err; echo "exit $?" >> gpurun_out/s_bench_dec.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ldb_inflate_decode' -s 1 -c 1 -o gpurun_out/prof_inflate_r02s python bench.py --workload decompress --chunks 65536 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/s_ncu_inflate.log 2>&1
+tail -3 gpurun_out/s_pytest.log; cat gpurun_out/s_bench_dec.json | python scripts/print_bench_line.py; tail -2 gpurun_out/s_bench_dec.err
