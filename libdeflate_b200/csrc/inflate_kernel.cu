@@ -107,11 +107,17 @@
 #define INF_SM_CNT     (INF_SM_SCRATCH)				// u32[16]
 #define INF_SM_CODE    (INF_SM_CNT + 64)			// u32[16]
 #define INF_SM_SUBBITS (INF_SM_CODE + 64)			// u8[1 << INF_LB]
+#ifndef INF_FUSE_OFF
+#define INF_FUSE_OFF 1		// a match's offset is decoded in the same step as its length when both fit
+#endif
 #ifndef INF_LIT2
-#define INF_LIT2 1		// decode a second literal in the same step when two follow each other
+#define INF_LIT2 4		// how many literals that follow a literal or a completed match are decoded in the same step
 #endif
 #define INF_SM_WQ      (INF_SM_SUBBITS + (1 << INF_LB))		// u32[32]: per-lane prefetched input word of the decode loop
-#define INF_SM_BYTES   (INF_SM_WQ + 128)				// per warp: 14720 with the default geometry
+#ifndef INF_WQ2
+#define INF_WQ2 0		// 1: two lookahead words per lane, one copy group per step (profiles/r02_inflate_d.md, call P)
+#endif
+#define INF_SM_BYTES   (INF_SM_WQ + 128 + 128 * INF_WQ2)		// per warp: 14720 with the default geometry
 #ifndef INF_WPC
 #define INF_WPC        5		// independent warps per CTA
 #endif
@@ -164,6 +170,7 @@ struct inf_lane {
 	u32 hlit, hdist, is_static;
 	u32 stored_len, stored_src;
 	u32 pend_len;		// decoded match length whose offset has not been decoded yet (ST_OFF)
+	u32 ri;			// INF_WQ2: which lookahead slot holds the word at wpos + 8
 	// bookkeeping
 	u32 chunk;		// chunk index
 	u32 hdr_bytes;		// wrapper header size
@@ -185,7 +192,12 @@ __device__ __forceinline__ void inf_cp_async4(u32 *smem_dst, const void *gsrc)
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void inf_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void inf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// everything but the copies of the most recent group (= the most recent decode step) has landed
+__device__ __forceinline__ void inf_cp_async_wait_older() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 #else
+__device__ __forceinline__ void inf_cp_async_commit() {}
+__device__ __forceinline__ void inf_cp_async_wait_older() {}
 __device__ __forceinline__ void inf_cp_async4(u32 *smem_dst, const void *gsrc) { *smem_dst = *(const u32 *)gsrc; }
 __device__ __forceinline__ void inf_cp_async_wait() {}
 #endif
@@ -746,22 +758,6 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	s.n_lit += put ? 1u : 0u;
 	if (put && (s.n_lit & 3) == 0) INF_ST_TOK((u32 *)(s.lit + s.n_lit - 4), s.acc);
 	const u32 vbits = bits >> cl;
-#if INF_LIT2
-	// A second literal in the same step: 72 % of the bench corpus' symbols are literals and they come in
-	// runs, so after a literal the next main-table entry is looked up at once and taken if it is a plain
-	// literal too (<= INF_LB bits, at least 17 valid bits are left in 'vbits').  Not near the end of the
-	// input (the tail rule above is evaluated per symbol start) and not when the output is full: those
-	// cases take the next step.
-	{
-		const u32 e2 = ((const u16 *)(sm + INF_SM_LTAB) + lane)[(vbits & ((1u << INF_LB) - 1)) * 32];
-		const bool put2 = put && e2 < LE_LEN_FLAG && s.wpos + 8 <= s.in_nal && s.n_lit != s.lit_limit;
-		const u32 acc3 = __funnelshift_r(s.acc, e2 >> 4, 8);
-		s.acc = put2 ? acc3 : s.acc;
-		s.n_lit += put2 ? 1u : 0u;
-		if (put2 && (s.n_lit & 3) == 0) INF_ST_TOK((u32 *)(s.lit + s.n_lit - 4), s.acc);
-		adv += put2 ? (e2 & 15) : 0u;
-	}
-#endif
 	// length or offset: base(slot) + extra bits, the same arithmetic up to k
 	const u32 slot = (e >> 4) & 31;
 	const u32 k = isoff ? 1 : 2;			// slots per doubling = 1 << k
@@ -774,31 +770,73 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	eb = len258 ? 0u : eb;
 	val += vbits & ((1u << eb) - 1);
 	adv += is_val ? eb : 0u;
-	s.bitpos += live ? adv : 0u;
 	const bool is_len = is_val && !isoff;
 	const bool is_offv = is_val && isoff;
 	// length: "no room" is decided before the offset is looked at (decompress_template.h:696-701)
 	const bool len_fits = val <= s.lit_limit - s.n_lit;
-	const bool off_ok = val <= inf_out_pos(s);
-	const bool emit = is_offv && off_ok;
+#if INF_FUSE_OFF
+	// The offset of a match in the SAME step as its length: after the follow-on literals two of three steps
+	// were the length / offset pairs of matches.  Taken when the offset's codeword sits in the main offset
+	// table and length + offset fit the 32 bits of 'bits' (nearly always); otherwise the next step is an
+	// ST_OFF step as before.  (The tail rule looks at litlen symbol starts only, so nothing changes there.)
+	const u32 obits = vbits >> eb;
+	const u32 eo = ((const u16 *)(sm + INF_SM_OTAB) + lane)[(obits & ((1u << INF_OB) - 1)) * 32];
+	const u32 clo = eo & 15, oslot = (eo >> 4) & 31;
+	const u32 ebo = oslot >= 4 ? (oslot - 2) >> 1 : 0;
+	const u32 valo = (oslot >= 4 ? 1 + ((2 + (oslot & 1)) << ebo) : 1 + oslot) + ((obits >> clo) & ((1u << ebo) - 1));
+	const bool fuse = is_len && len_fits && eo < LE_SUB_FLAG && adv + clo + ebo <= 32;
+	adv += fuse ? clo + ebo : 0u;
+#else
+	const bool fuse = false;
+	const u32 valo = 0, obits = 0, clo = 0, ebo = 0;
+#endif
+	const u32 m_len = fuse ? val : s.pend_len;
+	const u32 m_off = fuse ? valo : val;
+	const bool have_off = is_offv || fuse;
+	const bool off_ok = m_off <= inf_out_pos(s);
+	const bool emit = have_off && off_ok;
 	// the match record (and, before it, a literal-run record when more than 255 literals are pending)
 	const u32 litrun = s.n_lit - s.lit_mark;
 	const bool big = litrun > 255;
 	if (emit) {
 		u32 *r = s.rec_end - s.n_rec - 1;
 		if (big) { INF_ST_TOK(r, LDB_TOK_PURE_FLAG | litrun); r--; }
-		INF_ST_TOK(r, ((big ? 0u : litrun) << 23) | ((s.pend_len - 3) << 15) | (val - 1));
+		INF_ST_TOK(r, ((big ? 0u : litrun) << 23) | ((m_len - 3) << 15) | (m_off - 1));
 	}
 	s.n_rec += emit ? (big ? 2u : 1u) : 0u;
 	s.lit_mark = emit ? s.n_lit : s.lit_mark;
-	s.lit_limit -= emit ? s.pend_len : 0u;
-	s.pend_len = is_len ? val : s.pend_len;
+	s.lit_limit -= emit ? m_len : 0u;
+	const bool len_only = is_len && !fuse;		// the offset follows in the next step
+	s.pend_len = len_only ? val : s.pend_len;
+#if INF_LIT2
+	// A literal FOLLOWING this step's symbol is taken in the same step: 72 % of the bench corpus' symbols are
+	// literals, so after a literal, and after the offset that completes a match, the next main-table entry
+	// is looked up at once and taken if it is a plain literal (<= INF_LB bits; 'adv' <= 25 leaves them
+	// valid).  Not near the end of the input (the tail rule above is evaluated per symbol start) and not
+	// when the output is full: those cases take the next step.
+	{
+		u32 nbits = fuse ? obits >> (clo + ebo) : vbits >> (is_val ? eb : 0u);
+		bool more = put || emit;
+#pragma unroll
+		for (int x = 0; x < INF_LIT2; x++) {
+			const u32 e2 = ((const u16 *)(sm + INF_SM_LTAB) + lane)[(nbits & ((1u << INF_LB) - 1)) * 32];
+			more = more && e2 < LE_LEN_FLAG && adv <= 32 - INF_LB && s.wpos + 8 <= s.in_nal && s.n_lit != s.lit_limit;
+			const u32 acc3 = __funnelshift_r(s.acc, e2 >> 4, 8);
+			s.acc = more ? acc3 : s.acc;
+			s.n_lit += more ? 1u : 0u;
+			if (more && (s.n_lit & 3) == 0) INF_ST_TOK((u32 *)(s.lit + s.n_lit - 4), s.acc);
+			adv += more ? (e2 & 15) : 0u;
+			nbits >>= e2 & 15;
+		}
+	}
+#endif
+	s.bitpos += live ? adv : 0u;
 	// next state / verdict (the verdict is only read in ST_DONE)
 	u32 st = s.state, vd = s.verdict;
-	st = is_offv ? (off_ok ? (u32)ST_LIT : (u32)ST_DONE) : st;
-	vd = is_offv ? (u32)LDB_BAD_DATA : vd;
-	st = is_len ? (len_fits ? (u32)ST_OFF : (u32)ST_DONE) : st;
-	vd = is_len ? (u32)LDB_INSUFFICIENT_SPACE : vd;
+	st = have_off ? (off_ok ? (u32)ST_LIT : (u32)ST_DONE) : st;
+	vd = have_off ? (u32)LDB_BAD_DATA : vd;
+	st = len_only ? (len_fits ? (u32)ST_OFF : (u32)ST_DONE) : st;
+	vd = len_only ? (u32)LDB_INSUFFICIENT_SPACE : vd;
 	st = is_eob ? (s.is_final ? (u32)ST_DONE : (u32)ST_HEADER) : st;
 	vd = is_eob ? (u32)LDB_SUCCESS : vd;
 	st = lit_full ? (u32)ST_DONE : st;
@@ -811,6 +849,24 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	// in the lane's shared-memory slot wq: the next word is fetched into it by an asynchronous copy, so the
 	// load is tied to no register (held in a register, the compiler copied the word being loaded into the
 	// loop-carried register at the bottom of the loop and every step waited there: 10 % of the stall samples).
+#if INF_WQ2
+	// Two lookahead words per lane and one copy group per step: a refill waits only for groups older than
+	// the most recent one, and a word is used no earlier than two refills (>= two steps) after it was asked for.
+	inf_cp_async_commit();
+	const bool rf = act && s.bitpos >= 32;
+	if (rf) {
+		inf_cp_async_wait_older();
+		volatile u32 *slot = wq + 32 * s.ri;	// holds the word at wpos + 8
+		s.w0 = s.w1;
+		s.w1 = *slot;
+		s.wpos += 4;
+		s.bitpos -= 32;
+		const u32 pos = s.wpos + 12;		// the other slot holds wpos + 8 now; fetch the word after it
+		if (pos + 4 <= s.in_nal) inf_cp_async4((u32 *)slot, s.in_al + pos);
+		else *slot = inf_ld_word(s, pos);	// ragged end of the input: zero-padded word
+		s.ri ^= 1;
+	}
+#else
 	const bool rf = act && s.bitpos >= 32;
 	if (rf) {
 		inf_cp_async_wait();			// the word asked for ~3 steps ago
@@ -822,6 +878,7 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 		if (pos + 4 <= s.in_nal) inf_cp_async4(wq, s.in_al + pos);
 		else *(volatile u32 *)wq = inf_ld_word(s, pos);	// ragged end of the input: zero-padded word
 	}
+#endif
 }
 
 // ---- the decode kernel --------------------------------------------------------------
@@ -847,7 +904,7 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 	s.chunk = 0xffffffffu;
 	s.in = nullptr; s.in_al = nullptr; s.in_a0 = 0; s.in_n = 0; s.in_nal = 0; s.wpos = 0; s.w0 = 0; s.w1 = 0; s.w2 = 0; s.bitpos = 0;
 	s.lit = nullptr; s.rec_end = nullptr; s.n_lit = 0; s.n_rec = 0; s.lit_mark = 0; s.lit_limit = 0; s.out_avail = 0; s.acc = 0;
-	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.pend_len = 0;
+	s.is_final = 0; s.hlit = 0; s.hdist = 0; s.is_static = 0; s.stored_len = 0; s.stored_src = 0; s.hdr_bytes = 0; s.pend_len = 0; s.ri = 0;
 	bool exhausted = false;
 
 	// the bookkeeping of a stream that has ended (ST_DONE) with s.verdict; the lane becomes idle
@@ -1014,12 +1071,20 @@ ldb_inflate_decode_kernel(ldb_inflate_args a, u32 *work_counter)
 #pragma unroll 1
 		u32 *wq = (u32 *)(sm + INF_SM_WQ) + lane;
 		*(volatile u32 *)wq = s.w2;		// inside the loop the third window word lives in shared memory
+#if INF_WQ2
+		s.ri = 0;				// slot[ri] = word at wpos + 8, slot[ri ^ 1] = word at wpos + 12
+		*(volatile u32 *)(wq + 32) = s.state >= ST_LIT ? inf_ld_word(s, s.wpos + 12) : 0;
+#endif
 		for (int it = 0; it < INF_QUANTUM; it++) {
 			inf_decode_step(s, sm, ovf, lane, wq);
 			if ((it & 31) == 31 && !__any_sync(LDB_FULL_MASK, s.state >= ST_LIT)) break;
 		}
 		inf_cp_async_wait();
+#if INF_WQ2
+		s.w2 = *(volatile u32 *)(wq + 32 * s.ri);
+#else
 		s.w2 = *(volatile u32 *)wq;		// ... and outside of it in a register again
+#endif
 		__syncwarp();
 	}
 }

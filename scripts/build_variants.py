@@ -16,7 +16,11 @@ VARIANTS = {
     # decode table geometries at 448 B per lane (offline count of global overflow lookups per lane-step on the bench corpus:
     # default 0.35 %, g6 0.20 %, o5s48l16 0.22 %): g6 = -DINF_LSUB_SM=16 -DINF_OB=6 -DINF_OSUB_SM=16 16.73 ms,
     # o5s48l16 = -DINF_LSUB_SM=16 -DINF_OB=5 -DINF_OSUB_SM=48 16.68 ms vs 16.54 ms default -- dropped
-    "timing": ["-DLZ_TIMING"],          # in-kernel phase clocks of the deflate kernel (ldb_lz_timing_dump)
+    "timing": ["-DLZ_TIMING"],
+    # decode step, follow-on literals (INF_LIT2) at 65536 x 64 KiB: 0 / 1 / 2 / 3 / 4 -> 16.5 / 14.3 / 13.1 / 12.6 / 12.5 ms;
+    # with the two-slot asynchronous lookahead (-DINF_WQ2=1) 2 / 3 -> 13.8 / 13.0 ms (slower again)
+    "nofuse": ["-DINF_FUSE_OFF=0"],     # offset decoded in its own step (as before call V)
+    "fuse_lit3": ["-DINF_LIT2=2"],
 }
 # cache-streaming hints for the token stream off / 24 resolve warps per SM: no change / 10.5 ms (default 9.0)
 # decode kernel with more warps per SM (code lengths in global memory, smaller tables, register cap): 18 / 21 / 24 warps
