@@ -695,10 +695,11 @@ __device__ __forceinline__ u32 inf_static_litlen_len(u32 sym)
 
 #if defined(LDB_EMU) && defined(INF_STATS)
 // tuning aid of the emulator build only: {litlen sub in smem, litlen sub global, offset sub in smem, offset sub global, steps}
-unsigned long long inf_stats[8];
+// + step mix {8 literal first, 9 length + offset, 10 length only, 11 offset only, 12 end of block, 13 idle lane, 14 follow-on literals}
+unsigned long long inf_stats[16];
 extern "C" __attribute__((visibility("default"))) void ldb_inf_stats(unsigned long long *out, int reset)
 {
-	for (int i = 0; i < 8; i++) { out[i] = inf_stats[i]; if (reset) inf_stats[i] = 0; }
+	for (int i = 0; i < 16; i++) { out[i] = inf_stats[i]; if (reset) inf_stats[i] = 0; }
 }
 #endif
 
@@ -827,6 +828,9 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 			if (more && (s.n_lit & 3) == 0) INF_ST_TOK((u32 *)(s.lit + s.n_lit - 4), s.acc);
 			adv += more ? (e2 & 15) : 0u;
 			nbits >>= e2 & 15;
+#if defined(LDB_EMU) && defined(INF_STATS)
+			if (more) atomicAdd(&inf_stats[14], 1ull);
+#endif
 		}
 	}
 #endif
@@ -845,6 +849,12 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 	vd = dead ? (u32)LDB_BAD_DATA : vd;
 	s.state = st;
 	s.verdict = vd;
+#if defined(LDB_EMU) && defined(INF_STATS)
+	if (!act) atomicAdd(&inf_stats[13], 1ull);
+	else {
+		atomicAdd(&inf_stats[is_lit ? 8 : fuse ? 9 : len_only ? 10 : is_offv ? 11 : 12], 1ull);
+	}
+#endif
 	// refill for the NEXT step (bitpos < 32 afterwards).  Inside the decode loop the third window word lives
 	// in the lane's shared-memory slot wq: the next word is fetched into it by an asynchronous copy, so the
 	// load is tied to no register (held in a register, the compiler copied the word being loaded into the
