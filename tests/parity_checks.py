@@ -74,6 +74,37 @@ def check_decompress_valid(ctx, orc, streams):
         assert all(g[0] == 0 and g[1] == s[1] for g, s in zip(got, sel))
 
 
+def check_truncation_and_space_sweep(ctx, orc, n_text=6000):
+    """The decode step takes several symbols at once (a match's length and offset, up to four literals behind
+    a symbol).  What may NOT move with that: the over-read rule near the end of the input (evaluated per symbol
+    start, ref: lib/deflate_decompress.c:236-254) and the "no room" verdicts.  So: one text stream cut at every
+    byte of its last 48 bytes (plus a spread of earlier cuts), zero-extended, and every output size from a few
+    bytes short to a few bytes long -- verdict, byte counts and bytes against the oracle."""
+    plains = [corpus.text(n_text, 77), corpus.text(700, 78) + b"q" * 300 + corpus.text(500, 79), corpus.mixed(n_text, 80)]
+    streams, avails = [], []
+    for p in plains:
+        for lv, strat in ((6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_FIXED), (1, zlib.Z_HUFFMAN_ONLY)):
+            z = corpus.zlib_raw(p, lv, strat, -15)
+            cuts = sorted(set(list(range(max(0, len(z) - 48), len(z) + 1)) + list(range(1, len(z), max(1, len(z) // 23)))))
+            for c in cuts:
+                streams.append(z[:c]); avails.append(len(p))
+            for extra in (1, 2, 7, 9):
+                streams.append(z + bytes(extra)); avails.append(len(p))
+            for d in (-9, -5, -4, -3, -2, -1, 1, 3):
+                streams.append(z); avails.append(max(0, len(p) + d))
+    for exact in (False, True):
+        got = ctx.decompress_batch_host(streams, avails, 0, exact)
+        seen = set()
+        for z, a, g in zip(streams, avails, got):
+            r = orc.decompress(z, a, 0, exact)
+            seen.add(r[0])
+            if r[0] == 0:
+                assert g == r, ("sweep mismatch", exact, len(z), a, g[0], g[2:], r[2:])
+            else:
+                assert g[0] == r[0], ("sweep verdict mismatch", exact, len(z), a, g[0], r[0])
+        assert seen >= {0, 1, 3}, seen
+
+
 def check_decompress_large(ctx, sizes=(150000, 262144 + 123), levels=(0, 1, 6, 9)):
     """Chunks larger than the resolve kernel's 32 KiB window ring (several wraps), stored blocks longer
     than its staging span (the literal-run path), runs of equal bytes (offset 1, the periodic path)

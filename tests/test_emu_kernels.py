@@ -24,6 +24,10 @@ def test_gzip_optional_header_fields_emulated(emu_ctx, oracle, reflib):
     pc.check_gzip_optional_fields(emu_ctx, oracle, reflib)
 
 
+def test_inflate_truncation_and_space_sweep_emulated(emu_ctx, oracle):
+    pc.check_truncation_and_space_sweep(emu_ctx, oracle)
+
+
 def test_inflate_token_scratch_waves_emulated(emu_ctx, oracle):
     pc.check_decompress_in_waves(emu_ctx, oracle, n_chunks=40)
 

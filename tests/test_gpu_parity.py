@@ -159,6 +159,11 @@ def test_decompress_fuzz_verdicts(gpu_ctx, oracle):
     assert set(seen) == {0, 1, 2, 3}, seen
 
 
+def test_decompress_truncation_and_space_sweep(gpu_ctx, oracle):
+    """Every cut of the last 48 input bytes and every output size around the exact one (multi-symbol decode step)."""
+    pc.check_truncation_and_space_sweep(gpu_ctx, oracle)
+
+
 def test_known_answer_fixtures(gpu_ctx, oracle):
     """ref: programs/test_incomplete_codes.c, test_invalid_streams.c, test_overread.c --
     hand-assembled streams with expected bytes / verdicts (tests/golden/known_answer.json)."""
