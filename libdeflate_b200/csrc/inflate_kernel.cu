@@ -812,8 +812,9 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 #if INF_LIT2
 	// A literal FOLLOWING this step's symbol is taken in the same step: 72 % of the bench corpus' symbols are
 	// literals, so after a literal, and after the offset that completes a match, the next main-table entry
-	// is looked up at once and taken if it is a plain literal (<= INF_LB bits; 'adv' <= 25 leaves them
-	// valid).  Not near the end of the input (the tail rule above is evaluated per symbol start) and not
+	// is looked up at once and taken if it is a plain literal whose codeword still lies inside the 32 bits of
+	// 'bits' (an entry is determined by the bits of its own codeword, so the check after the lookup is
+	// exact).  Not near the end of the input (the tail rule above is evaluated per symbol start) and not
 	// when the output is full: those cases take the next step.
 	{
 		u32 nbits = fuse ? obits >> (clo + ebo) : vbits >> (is_val ? eb : 0u);
@@ -821,7 +822,7 @@ __device__ __forceinline__ void inf_decode_step(inf_lane &s, const u8 *sm, const
 #pragma unroll
 		for (int x = 0; x < INF_LIT2; x++) {
 			const u32 e2 = ((const u16 *)(sm + INF_SM_LTAB) + lane)[(nbits & ((1u << INF_LB) - 1)) * 32];
-			more = more && e2 < LE_LEN_FLAG && adv <= 32 - INF_LB && s.wpos + 8 <= s.in_nal && s.n_lit != s.lit_limit;
+			more = more && e2 < LE_LEN_FLAG && adv + (e2 & 15) <= 32 && s.wpos + 8 <= s.in_nal && s.n_lit != s.lit_limit;
 			const u32 acc3 = __funnelshift_r(s.acc, e2 >> 4, 8);
 			s.acc = more ? acc3 : s.acc;
 			s.n_lit += more ? 1u : 0u;

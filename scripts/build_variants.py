@@ -21,6 +21,9 @@ VARIANTS = {
     # with the two-slot asynchronous lookahead (-DINF_WQ2=1) 2 / 3 -> 13.8 / 13.0 ms (slower again)
     "nofuse": ["-DINF_FUSE_OFF=0"],     # offset decoded in its own step (as before call V)
     "fuse_lit3": ["-DINF_LIT2=2"],
+    "lit6": ["-DINF_LIT2=6"],           # up to six follow-on literals (default four)
+    "g6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16"],      # 6-bit main offset table: more matches take the fused path
+    "g6lit6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16", "-DINF_LIT2=6"],
 }
 # cache-streaming hints for the token stream off / 24 resolve warps per SM: no change / 10.5 ms (default 9.0)
 # decode kernel with more warps per SM (code lengths in global memory, smaller tables, register cap): 18 / 21 / 24 warps

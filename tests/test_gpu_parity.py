@@ -221,6 +221,26 @@ def test_bgzf(gpu_ctx):
     pc.check_bgzf(gpu_ctx, sizes=(0, 1, 65279, 65280, 65281, 200000, 3000000), levels=(1, 6, 9))
 
 
+def test_gz_front_end(gpu_ctx, gpu_api, tmp_path):
+    """python -m libdeflate_b200.gz (gzip-style front end) on the GPU: what it writes is read by
+    Python's gzip, what it reads back is identical, blocked and plain multi-member files both decode."""
+    import gzip
+    import corpus
+    from libdeflate_b200 import gz
+    data = corpus.text(3000000, 9) + corpus.rand(70000, 9) + corpus.zeros(100000)
+    f = tmp_path / "a.bin"
+    f.write_bytes(data)
+    assert gz.main(["-6", "-k", str(f)], ctx=gpu_ctx) == 0
+    packed = (tmp_path / "a.bin.gz").read_bytes()
+    assert gzip.decompress(packed) == data and gz.uncompressed_size(packed) == len(data)
+    f.unlink()
+    assert gz.main(["-d", str(tmp_path / "a.bin.gz")], ctx=gpu_ctx) == 0
+    assert f.read_bytes() == data
+    assert gz.decompress_bytes(gpu_ctx, pc.bgzf_reference_file(data)) == data
+    plain = gzip.compress(data[:700000], 6) + gzip.compress(b"") + gzip.compress(data[700000:], 1)
+    assert gz.decompress_members(gpu_api, plain) == data
+
+
 def test_pipelined_host_path(gpu_ctx):
     import libdeflate_b200 as ldb
     pc.check_host_pipeline(ldb.lib(), gpu_ctx, n=8192, chunk=65536)
