@@ -21,6 +21,7 @@ VARIANTS = {
     # with the two-slot asynchronous lookahead (-DINF_WQ2=1) 2 / 3 -> 13.8 / 13.0 ms (slower again)
     "nofuse": ["-DINF_FUSE_OFF=0"],     # offset decoded in its own step (as before call V)
     "fuse_lit3": ["-DINF_LIT2=2"],
+    # call W, on top of the fused step (default 10.14 ms): lit6 10.28, g6 10.20, g6lit6 10.27 -- no difference
     "lit6": ["-DINF_LIT2=6"],           # up to six follow-on literals (default four)
     "g6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16"],      # 6-bit main offset table: more matches take the fused path
     "g6lit6": ["-DINF_LSUB_SM=16", "-DINF_OB=6", "-DINF_OSUB_SM=16", "-DINF_LIT2=6"],
