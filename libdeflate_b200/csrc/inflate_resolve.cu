@@ -37,7 +37,8 @@
 #ifndef RES_LIT_FAST
 #define RES_LIT_FAST 16u	// literal runs up to this are placed by the owning lane in one step
 #endif
-#define RES_SM_BYTES RES_STG
+#define RES_SLACK   32u		// bytes behind the ring's end that a piece may run into (res_store16)
+#define RES_SM_BYTES (RES_STG + RES_SLACK)
 // token records are read exactly once: cache-streaming loads (evict-first) keep them from displacing the
 // window rows in L2
 #ifndef RES_STREAM_HINTS
@@ -106,30 +107,37 @@ int ldb_launch_inflate_caps(const size_t *d_in_nbytes, const size_t *d_out_avail
 // Stores the first m (<= 16) bytes of the little-endian words v0..v3 at staging position qd:
 // single bytes up to the next word boundary, whole words, single bytes again.  Only bytes
 // [qd, qd + m) are written, so neighbouring lanes never touch each other's bytes.
+// The ring has RES_SLACK bytes behind its end: a piece is written from its wrapped start address
+// without wrapping every store (one address + immediates instead of an add and a mask per store);
+// the one piece per 4 KiB that runs past the end folds its overhang back to the ring's start itself.
 __device__ __forceinline__ void res_store16(u8 *stg, u32 qd, u32 m, u32 v0, u32 v1, u32 v2, u32 v3)
 {
+	const u32 base = qd & RES_SMASK;
+	u8 *d = stg + base;
 	u32 h = (4 - (qd & 3)) & 3;
 	if (h > m) h = m;
-	if (h > 0) stg[qd & RES_SMASK] = (u8)v0;
-	if (h > 1) stg[(qd + 1) & RES_SMASK] = (u8)(v0 >> 8);
-	if (h > 2) stg[(qd + 2) & RES_SMASK] = (u8)(v0 >> 16);
+	if (h > 0) d[0] = (u8)v0;
+	if (h > 1) d[1] = (u8)(v0 >> 8);
+	if (h > 2) d[2] = (u8)(v0 >> 16);
 	const u32 hsh = 8 * h;
 	u32 u0 = __funnelshift_r(v0, v1, hsh), u1 = __funnelshift_r(v1, v2, hsh);
 	u32 u2 = __funnelshift_r(v2, v3, hsh), u3 = v3 >> hsh;
-	u32 *d32 = (u32 *)stg;
-	const u32 qa = qd + h, rem = m - h, nw = rem >> 2;
-	if (nw > 0) d32[(qa & RES_SMASK) >> 2] = u0;
-	if (nw > 1) d32[((qa + 4) & RES_SMASK) >> 2] = u1;
-	if (nw > 2) d32[((qa + 8) & RES_SMASK) >> 2] = u2;
-	if (nw > 3) d32[((qa + 12) & RES_SMASK) >> 2] = u3;
+	u32 *d32 = (u32 *)(d + h);
+	const u32 rem = m - h, nw = rem >> 2;
+	if (nw > 0) d32[0] = u0;
+	if (nw > 1) d32[1] = u1;
+	if (nw > 2) d32[2] = u2;
+	if (nw > 3) d32[3] = u3;
 	const u32 t = rem & 3;
 	if (t) {
 		u32 tw = nw == 0 ? u0 : (nw == 1 ? u1 : (nw == 2 ? u2 : u3));
-		const u32 qt = qa + 4 * nw;
-		stg[qt & RES_SMASK] = (u8)tw;
-		if (t > 1) stg[(qt + 1) & RES_SMASK] = (u8)(tw >> 8);
-		if (t > 2) stg[(qt + 2) & RES_SMASK] = (u8)(tw >> 16);
+		u8 *t8 = d + h + 4 * nw;
+		t8[0] = (u8)tw;
+		if (t > 1) t8[1] = (u8)(tw >> 8);
+		if (t > 2) t8[2] = (u8)(tw >> 16);
 	}
+	if (base + m > RES_STG)
+		for (u32 k = RES_STG; k < base + m; k++) stg[k - RES_STG] = stg[k];
 }
 
 // m <= 16 bytes from window position qs (committed bytes: the chunk's own output, read back
